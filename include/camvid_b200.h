@@ -1,0 +1,205 @@
+/*
+ * camvid_b200.h -- C ABI of libcamvid_b200.so: the sm_100a (B200) kernels behind the UNet / SegNet
+ * training + eval hot path of weiaicunzai/pytorch-camvid.
+ *
+ * The reference has no FFI layer: its hot path is a chain of ATen calls made from nn.Modules.  Each entry point
+ * below therefore cites the reference call site (file:line in the reference tree) whose ATen op it replaces;
+ * INTEGRATION.md shows the ctypes / torch.library binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in `_host`. The library never allocates, frees or
+ *     retains caller memory; workspaces are passed in (sizes from the cvb_*_workspace_bytes helpers).
+ *   - Activations are NHWC bf16 "views": channel stride 1, explicit element strides for N, H, W so that a view can
+ *     be a channel slice of a concat buffer or a 44-row window of a 45-row buffer (UNet F.pad, models/unet.py:120-123).
+ *     View base pointers must be 16-byte aligned, C a multiple of 8, strides multiples of 8 elements.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - Return value: 0 on success, negative cvb_status on error; cvb_last_error() returns a thread-local message.
+ *     Nothing throws across this boundary. All functions are re-entrant (forward is called from the Python main
+ *     thread, backward from autograd's per-device worker thread).
+ */
+#ifndef CAMVID_B200_H_
+#define CAMVID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CVB_API __attribute__((visibility("default")))
+#else
+#define CVB_API
+#endif
+
+typedef enum {
+  CVB_OK = 0,
+  CVB_ERR_INVALID_ARG = -1,   /* shape / alignment / null pointer */
+  CVB_ERR_UNSUPPORTED = -2,   /* valid request the kernels do not cover (e.g. C not multiple of 64 for the GEMMs) */
+  CVB_ERR_CUDA = -3,          /* a CUDA runtime / driver call failed */
+  CVB_ERR_NO_DEVICE = -4      /* no sm_100 device */
+} cvb_status;
+
+/* NHWC bf16 view. Element (n,h,w,c) lives at ptr[n*sn + h*sh + w*sw + c]. */
+typedef struct {
+  void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+} cvb_view;
+
+CVB_API const char* cvb_last_error(void);
+CVB_API int cvb_abi_version(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+CVB_API int cvb_sm_count(void);
+/* Releases library-owned host state (nothing on the device is owned). */
+CVB_API void cvb_shutdown(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layout conversion at the nn.Module boundary (reference tensors are NCHW fp32: train.py:126-128).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 [n,c_src,h,w] -> NHWC bf16 view; channels c_src..dst.c-1 of the view are written as zero. */
+CVB_API int cvb_nchw_f32_to_nhwc_bf16(const float* src, int c_src, cvb_view dst, void* stream);
+/* NHWC bf16 view (first c_dst channels) -> NCHW fp32 [n,c_dst,h,w]. */
+CVB_API int cvb_nhwc_bf16_to_nchw_f32(cvb_view src, float* dst, int c_dst, void* stream);
+/* First-layer im2col (models/unet.py:41 / models/segnet.py:24 have Cin=3): NCHW fp32 [n,c_src,h,w] ->
+ * NHWC bf16 view with channel k = ci*9 + r*3 + s holding x[n, ci, h+r-1, w+s-1] (zero outside), k >= 9*c_src zero.
+ * Turns the K=27 convolution into a single-tap GEMM whose weight matrix is the OIHW tensor flattened. */
+CVB_API int cvb_im2col3x3_nchw_f32(const float* src, int c_src, cvb_view dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * 3x3 / stride 1 / pad 1 convolution as implicit GEMM on tcgen05 (nn.Conv2d(.,.,3,padding=1): models/unet.py:11,
+ * models/segnet.py:8).  bf16 operands, fp32 accumulation in TMEM, TMA-fed.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Packs OIHW fp32 weights [cout,cin,3,3] into the bf16 GEMM-B matrix of the forward conv:
+ * dst[co][tap][ci] with co padded to cout_pad, ci to cin_pad (zeros), tap = r*3+s.   taps==1: dst[co][k], k=cin*9
+ * flattened OIHW padded to cin_pad (pairs with cvb_im2col3x3_nchw_f32). */
+CVB_API int cvb_pack_weights_fprop(const float* w, int cout, int cin, int taps, int cout_pad, int cin_pad, void* dst,
+                           void* stream);
+/* Packs the same weights for the data-gradient conv (aten::convolution_backward input grad):
+ * dst[ci][tap'][co] = w[co][ci][2-r][2-s], tap' = r*3+s, ci padded to cin_pad, co to cout_pad. */
+CVB_API int cvb_pack_weights_dgrad(const float* w, int cout, int cin, int cout_pad, int cin_pad, void* dst, void* stream);
+
+/* Epilogue selection for cvb_conv3x3_fprop. */
+typedef struct {
+  /* train mode: per-CTA partial sums for BatchNorm batch statistics, fp32 [cvb_conv_stat_rows()][2][y.c]
+   * (sum, sum of squares over valid pixels). NULL = not produced. */
+  float* stat_partials;
+  /* eval mode (BatchNorm folded, models/unet.py:12 with running stats): y = relu?(acc*scale[c] + shift[c]).
+   * NULL = store the raw accumulator. */
+  const float* scale;
+  const float* shift;
+  int32_t relu;
+} cvb_conv_epilogue;
+
+/* Rows of the stat_partials buffer the conv writes (== its grid size; depends only on the device). */
+CVB_API int cvb_conv_stat_rows(void);
+/* y[n,h,w,co] = sum_{tap,ci} x[n,h+r-1,w+s-1,ci] * wpack[co][tap][ci]   (taps = 9, or 1 for a 1x1 GEMM).
+ * x.c must equal cin_pad (multiple of 64), y.c == cout_pad (multiple of 64). The same entry point computes the
+ * data gradient when given dy as `x` and the cvb_pack_weights_dgrad matrix. */
+CVB_API int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_view y, const cvb_conv_epilogue* ep, void* stream);
+
+/* Weight gradient (aten::convolution_backward weight grad): dw[co][ci][r][s] = sum_{n,h,w} dy[n,h,w,co] *
+ * x[n,h+r-1,w+s-1,ci], written as OIHW fp32 [cout,cin,3,3] (taps==1: [cout, cin9] with x the im2col view).
+ * `workspace` holds split-K partial tiles; size from cvb_conv3x3_wgrad_workspace_bytes. */
+CVB_API int64_t cvb_conv3x3_wgrad_workspace_bytes(cvb_view x, cvb_view dy, int taps);
+CVB_API int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, int cout, int cin, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d (+ReLU) in training mode (nn.BatchNorm2d + nn.ReLU: models/unet.py:12-13, models/segnet.py:9-10).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Per-channel partial sums of a view (used when the producer did not emit them): partials fp32 [rows][2][c]. */
+CVB_API int cvb_bn_stats(cvb_view y, float* partials, int rows, void* stream);
+/* Reduces `rows` partial rows over `count` elements per channel and produces, for the first c channels:
+ *   mean, invstd = 1/sqrt(var_biased + eps), scale = gamma*invstd, shift = beta - mean*scale  (fp32 [c] each);
+ * if running_mean != NULL updates running stats like torch (momentum, unbiased variance), adding conv_bias to the
+ * mean when given (the conv kernels skip the bias: it cancels under batch statistics).
+ * Channels [c, c_pad) get scale = shift = 0 so padded lanes stay zero. */
+CVB_API int cvb_bn_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
+                    const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                    float momentum, float eps, float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* a = relu(y*scale + shift). */
+CVB_API int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, void* stream);
+/* Backward pass 1: g = da * [y*scale+shift > 0]; partials fp32 [rows][2][c] of (sum g, sum g*y). */
+CVB_API int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scale, const float* shift, float* partials,
+                           int rows, void* stream);
+/* Backward finalize: dgamma, dbeta (fp32 [c]) and the per-channel coefficients (coef fp32 [3][c_pad]) with
+ * dy = g*coef0 + y*coef1 + coef2 used by cvb_bn_relu_bwd_apply. */
+CVB_API int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
+                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
+                        void* stream);
+/* Backward pass 2: dy = (da*[a>0])*coef0 + y*coef1 + coef2  (bf16 view). */
+CVB_API int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale, const float* shift, const float* coef,
+                          cvb_view dy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MaxPool2d(2,2) with indices / MaxUnpool2d(2)  (models/unet.py:92, models/segnet.py:79-80).
+ * Index code: uint8 per output element, 0..3 = (dh*2+dw) of the FIRST maximum in scan order (0,0),(0,1),(1,0),(1,1),
+ * NaN wins over anything and the LAST NaN wins (torch's `val > max || isnan(val)` rule).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* out[n,ho,wo,c] = max over the 2x2 window (floor mode: ho = h/2, wo = w/2). code may be NULL. */
+CVB_API int cvb_maxpool2x2_fwd(cvb_view x, cvb_view out, uint8_t* code, void* stream);
+/* Same, with the BatchNorm+ReLU of the producer fused in: a = relu(y*scale+shift) is written to `a` and pooled. */
+CVB_API int cvb_bn_relu_maxpool2x2_fwd(cvb_view y, const float* scale, const float* shift, cvb_view a, cvb_view out,
+                               uint8_t* code, void* stream);
+/* dx[window] = dout at the coded position, 0 elsewhere; rows/cols outside any window (odd h/w) get 0.
+ * accumulate != 0: dx += instead (UNet skip connection + pool path). code == NULL: recompute argmax from x. */
+CVB_API int cvb_maxpool2x2_bwd(cvb_view dout, const uint8_t* code, cvb_view x_or_null, cvb_view dx, int accumulate,
+                       void* stream);
+/* out (size given by the view, models/segnet.py:104 output_size=) = zeros, out[window pos by code] = x. */
+CVB_API int cvb_maxunpool2x2_fwd(cvb_view x, const uint8_t* code, cvb_view out, void* stream);
+/* dx[n,ho,wo,c] = dout at the coded position. */
+CVB_API int cvb_maxunpool2x2_bwd(cvb_view dout, const uint8_t* code, cvb_view dx, void* stream);
+/* Parity export: torch-style int64 flat indices (h*W + w per (n,c) plane, NCHW [n,c,ho,wo]) from the codes. */
+CVB_API int cvb_pool_code_to_index(const uint8_t* code, int n, int ho, int wo, int c, int w_in, int64_t* idx_nchw,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)  (models/unet.py:25,29)
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream);
+CVB_API int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * nn.CrossEntropyLoss() forward + backward fused (train.py:105,130-131; eval.py:42,58): mean over counted pixels.
+ * logits: NCHW fp32 [n,c,h,w] (the module boundary); target int64 [n,h,w].
+ * loss_sum_count: double [2], ACCUMULATED into (caller zeroes): sum of -log p[target], number of counted pixels.
+ *   A pixel is counted when target != ignore_index and 0 <= target < c (torch asserts on other values; here they
+ *   are skipped).
+ * dlogits (may be NULL): same layout as logits, receives (softmax - onehot) * gs, 0 for skipped pixels, where
+ *   gs = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)  -- pass 1/count on the host when nothing is ignored,
+ *   or a device scalar computed from the target when ignore_index is in use.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_softmax_ce_nchw_f32(const float* logits, const int64_t* target, int n, int c, int h, int w,
+                            int64_t ignore_index, double* loss_sum_count, float* dlogits, float grad_scale,
+                            const float* grad_scale_dev, void* stream);
+/* Same on the model's internal NHWC bf16 logits view (first c channels); dlogits (ptr may be NULL) is an NHWC bf16
+ * view whose channels >= c are written as zero. */
+CVB_API int cvb_softmax_ce_nhwc_bf16(cvb_view logits, int c, const int64_t* target, int64_t ignore_index,
+                             double* loss_sum_count, cvb_view dlogits, float grad_scale, const float* grad_scale_dev,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * preds.argmax(dim=1) + confusion matrix (train.py:191-194, utils.py:162-228, legacy/metrics.py:22-30).
+ * cm: int64 [c][c], rows = ground truth, cols = prediction, ACCUMULATED into (caller zeroes). Labels outside
+ * [0,c) are skipped (sklearn `labels=range(C)` semantics).
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c, int64_t* cm, void* stream);
+/* Fused: first-max argmax over c channels of NCHW fp32 logits; optionally also writes pred (int64 [n,h,w]). */
+CVB_API int cvb_argmax_confusion_nchw_f32(const float* logits, const int64_t* gt, int n, int c, int h, int w,
+                                  int64_t* pred_or_null, int64_t* cm, void* stream);
+CVB_API int cvb_argmax_confusion_nhwc_bf16(cvb_view logits, int c, const int64_t* gt, int64_t* pred_or_null, int64_t* cm,
+                                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Utilities
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Zero-fills a bf16 view (pad rows of concat buffers). */
+CVB_API int cvb_zero_view(cvb_view v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAMVID_B200_H_ */

@@ -1,0 +1,300 @@
+// BatchNorm2d(+ReLU) training-mode kernels on NHWC bf16 views (reference: models/unet.py:12-13, models/segnet.py:9-10).
+// All HBM-bound: 128-bit accesses, one thread = 8 channels of one pixel, fp32 math.
+#include "common.cuh"
+
+namespace cvb {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-channel reductions: every block strides over pixels, each thread owns one 8-channel group, partial sums are
+// combined in shared memory and written as one row of partials[row][2][C].
+//   MODE 0: (sum y, sum y^2)                         -- batch statistics
+//   MODE 1: g = da*[y*scale+shift > 0]; (sum g, sum g*y) -- BatchNorm+ReLU backward reduction
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              float* __restrict__ partials) {
+  extern __shared__ float red[];  // [kThreads][16]
+  const int CV = y.c >> 3;
+  const int ppb = kThreads / CV;  // pixels handled per block iteration (CV divides kThreads, checked on host)
+  const int cv = threadIdx.x % CV;
+  const int pl = threadIdx.x / CV;
+  const long long npix = 1LL * y.n * y.h * y.w;
+
+  float s1[8], s2[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (MODE == 1) {
+    ld8f(scale + cv * 8, sc);
+    ld8f(shift + cv * 8, sh);
+  }
+  for (long long pix = 1LL * blockIdx.x * ppb + pl; pix < npix; pix += 1LL * gridDim.x * ppb) {
+    int w = static_cast<int>(pix % y.w);
+    long long t = pix / y.w;
+    int h = static_cast<int>(t % y.h);
+    int n = static_cast<int>(t / y.h);
+    float fy[8];
+    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), fy);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += fy[j];
+        s2[j] = fmaf(fy[j], fy[j], s2[j]);
+      }
+    } else {
+      float fd[8];
+      unpack8(ldg16(da.p + voff(da, n, h, w) + cv * 8), fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+        s1[j] += g;
+        s2[j] = fmaf(g, fy[j], s2[j]);
+      }
+    }
+  }
+  float* mine = red + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = s1[j];
+    mine[8 + j] = s2[j];
+  }
+  __syncthreads();
+  // thread t < 2*C sums column t over the ppb pixel lanes
+  const int C = y.c;
+  for (int o = threadIdx.x; o < 2 * C; o += kThreads) {
+    int which = o / C;  // 0: s1, 1: s2
+    int c = o % C;
+    int ocv = c >> 3, oj = c & 7;
+    float acc = 0.f;
+    for (int l = 0; l < ppb; ++l) acc += red[(l * CV + ocv) * 16 + which * 8 + oj];
+    partials[(1LL * blockIdx.x * 2 + which) * C + c] = acc;
+  }
+}
+
+static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
+  int CV = v.c / 8;
+  CVB_REQUIRE(CV <= kThreads && (kThreads % CV) == 0, CVB_ERR_UNSUPPORTED,
+              "bn reduce: channels %d must divide %d", v.c, kThreads * 8);
+  CVB_REQUIRE(rows > 0, CVB_ERR_INVALID_ARG, "bn reduce: rows must be positive");
+  *grid = rows;
+  return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// finalize kernels: tiny, one thread per channel, double accumulation over the partial rows
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride,
+                                   double inv_count, double unbias, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                   float* running_mean, float* running_var, float momentum, float eps, float* mean,
+                                   float* invstd, float* scale, float* shift) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c_pad) return;
+  if (ch >= c) {
+    scale[ch] = 0.f;
+    shift[ch] = 0.f;
+    if (mean) mean[ch] = 0.f;
+    if (invstd) invstd[ch] = 0.f;
+    return;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s1 += static_cast<double>(partials[(2LL * r) * pstride + ch]);
+    s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
+  }
+  double m = s1 * inv_count;
+  double var = s2 * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  float sc = gamma[ch] * is;
+  mean[ch] = static_cast<float>(m);
+  invstd[ch] = is;
+  scale[ch] = sc;
+  shift[ch] = beta[ch] - static_cast<float>(m) * sc;
+  if (running_mean) {
+    float mb = static_cast<float>(m) + (conv_bias ? conv_bias[ch] : 0.f);
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mb;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(var * unbias);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride,
+                                       double inv_count, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       float* dgamma, float* dbeta, float* coef) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c_pad) return;
+  if (ch >= c) {
+    coef[ch] = 0.f;
+    coef[c_pad + ch] = 0.f;
+    coef[2 * c_pad + ch] = 0.f;
+    return;
+  }
+  double sg = 0.0, sgy = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    sg += static_cast<double>(partials[(2LL * r) * pstride + ch]);
+    sgy += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
+  }
+  double m = mean[ch], is = invstd[ch], g = gamma[ch];
+  double dg = is * (sgy - m * sg);  // sum g * xhat
+  double db = sg;
+  dgamma[ch] = static_cast<float>(dg);
+  dbeta[ch] = static_cast<float>(db);
+  double sc = g * is;
+  // dy = sc*g - sc*db/N - sc*(y-m)*is*dg/N
+  coef[ch] = static_cast<float>(sc);
+  coef[c_pad + ch] = static_cast<float>(-sc * is * dg * inv_count);
+  coef[2 * c_pad + ch] = static_cast<float>(-sc * db * inv_count + sc * m * is * dg * inv_count);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// apply kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(View y, View a, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift) {
+  const int CV = y.c >> 3;
+  const long long total = 1LL * y.n * y.h * y.w * CV;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    int cv = static_cast<int>(i % CV);
+    long long pix = i / CV;
+    int w = static_cast<int>(pix % y.w);
+    long long t = pix / y.w;
+    int h = static_cast<int>(t % y.h);
+    int n = static_cast<int>(t / y.h);
+    float f[8], sc[8], sh[8];
+    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), f);
+    ld8f(scale + cv * 8, sc);
+    ld8f(shift + cv * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    stg16(a.p + voff(a, n, h, w) + cv * 8, pack8(f));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, View y, View dy,
+                                                                      const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift,
+                                                                      const float* __restrict__ coef, int c_pad) {
+  const int CV = y.c >> 3;
+  const long long total = 1LL * y.n * y.h * y.w * CV;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    int cv = static_cast<int>(i % CV);
+    long long pix = i / CV;
+    int w = static_cast<int>(pix % y.w);
+    long long t = pix / y.w;
+    int h = static_cast<int>(t % y.h);
+    int n = static_cast<int>(t / y.h);
+    float fy[8], fd[8], sc[8], sh[8], c0[8], c1[8], c2[8], o[8];
+    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), fy);
+    unpack8(ldg16(da.p + voff(da, n, h, w) + cv * 8), fd);
+    ld8f(scale + cv * 8, sc);
+    ld8f(shift + cv * 8, sh);
+    ld8f(coef + cv * 8, c0);
+    ld8f(coef + c_pad + cv * 8, c1);
+    ld8f(coef + 2 * c_pad + cv * 8, c2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+      o[j] = fmaf(g, c0[j], fmaf(fy[j], c1[j], c2[j]));
+    }
+    stg16(dy.p + voff(dy, n, h, w) + cv * 8, pack8(o));
+  }
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" int cvb_bn_stats(cvb_view y, float* partials, int rows, void* stream) {
+  int rc = check_view(y, "bn_stats.y");
+  if (rc) return rc;
+  CVB_REQUIRE(partials, CVB_ERR_INVALID_ARG, "bn_stats: null partials");
+  int grid;
+  rc = reduce_launch_cfg(y, rows, &grid);
+  if (rc) return rc;
+  View vy = to_dev(y);
+  bn_reduce_kernel<0><<<grid, kThreads, kThreads * 16 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      vy, vy, nullptr, nullptr, partials);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scale, const float* shift,
+                                      float* partials, int rows, void* stream) {
+  int rc = check_view(y, "bn_bwd_reduce.y");
+  if (rc) return rc;
+  rc = check_view(da, "bn_bwd_reduce.da");
+  if (rc) return rc;
+  CVB_REQUIRE(same_shape(da, y), CVB_ERR_INVALID_ARG, "bn_bwd_reduce: da and y shapes differ");
+  CVB_REQUIRE(scale && shift && partials, CVB_ERR_INVALID_ARG, "bn_bwd_reduce: null pointer");
+  int grid;
+  rc = reduce_launch_cfg(y, rows, &grid);
+  if (rc) return rc;
+  bn_reduce_kernel<1><<<grid, kThreads, kThreads * 16 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      to_dev(y), to_dev(da), scale, shift, partials);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
+                               const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                               float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                               void* stream) {
+  CVB_REQUIRE(partials && gamma && beta && mean && invstd && scale && shift, CVB_ERR_INVALID_ARG,
+              "bn_finalize: null pointer");
+  CVB_REQUIRE(rows > 0 && c > 0 && c_pad >= c && count > 0, CVB_ERR_INVALID_ARG, "bn_finalize: bad sizes");
+  CVB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CVB_ERR_INVALID_ARG,
+              "bn_finalize: running_mean and running_var must both be given or both be NULL");
+  double inv = 1.0 / static_cast<double>(count);
+  double unbias = count > 1 ? static_cast<double>(count) / static_cast<double>(count - 1) : 1.0;
+  bn_finalize_kernel<<<(c_pad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, rows, c, c_pad, c_pad, inv, unbias, gamma, beta, conv_bias, running_mean, running_var, momentum, eps,
+      mean, invstd, scale, shift);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c_pad, int64_t count,
+                                   const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                                   float* dbeta, float* coef, void* stream) {
+  CVB_REQUIRE(partials && gamma && mean && invstd && dgamma && dbeta && coef, CVB_ERR_INVALID_ARG,
+              "bn_bwd_finalize: null pointer");
+  CVB_REQUIRE(rows > 0 && c > 0 && c_pad >= c && count > 0, CVB_ERR_INVALID_ARG, "bn_bwd_finalize: bad sizes");
+  bn_bwd_finalize_kernel<<<(c_pad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, rows, c, c_pad, c_pad, 1.0 / static_cast<double>(count), gamma, mean, invstd, dgamma, dbeta, coef);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, void* stream) {
+  int rc = check_view(y, "bn_relu_apply.y");
+  if (rc) return rc;
+  rc = check_view(a, "bn_relu_apply.a");
+  if (rc) return rc;
+  CVB_REQUIRE(same_shape(y, a), CVB_ERR_INVALID_ARG, "bn_relu_apply: shapes differ");
+  CVB_REQUIRE(scale && shift, CVB_ERR_INVALID_ARG, "bn_relu_apply: null scale/shift");
+  long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
+  bn_relu_apply_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      to_dev(y), to_dev(a), scale, shift);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale, const float* shift,
+                                     const float* coef, cvb_view dy, void* stream) {
+  int rc = check_view(y, "bn_bwd_apply.y");
+  if (rc) return rc;
+  rc = check_view(da, "bn_bwd_apply.da");
+  if (rc) return rc;
+  rc = check_view(dy, "bn_bwd_apply.dy");
+  if (rc) return rc;
+  CVB_REQUIRE(same_shape(y, da) && same_shape(y, dy), CVB_ERR_INVALID_ARG, "bn_bwd_apply: shapes differ");
+  CVB_REQUIRE(scale && shift && coef, CVB_ERR_INVALID_ARG, "bn_bwd_apply: null pointer");
+  long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
+  bn_relu_bwd_apply_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}

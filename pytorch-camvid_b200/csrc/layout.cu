@@ -1,0 +1,203 @@
+// Layout conversion at the nn.Module boundary (NCHW fp32 <-> NHWC bf16), first-layer im2col, weight packing for the
+// implicit-GEMM convolutions and view zero-fill. Memory-bound; pixel-fastest thread mapping keeps the NCHW side
+// coalesced, each thread moves one 16-byte NHWC vector.
+#include "common.cuh"
+
+namespace cvb {
+
+constexpr int kThreads = 256;
+
+// thread = (pixel, 8-channel group); consecutive threads = consecutive pixels (coalesced plane reads)
+__global__ void __launch_bounds__(kThreads) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int c_src,
+                                                                          View dst) {
+  const int CV = dst.c >> 3;
+  const long long hw = 1LL * dst.h * dst.w;
+  const long long total = 1LL * dst.n * hw * CV;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    long long p = i % hw;
+    long long t = i / hw;
+    int cv = static_cast<int>(t % CV);
+    int n = static_cast<int>(t / CV);
+    int h = static_cast<int>(p / dst.w), w = static_cast<int>(p % dst.w);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cv * 8 + j;
+      f[j] = c < c_src ? __ldg(src + (1LL * n * c_src + c) * hw + p) : 0.f;
+    }
+    stg16(dst.p + voff(dst, n, h, w) + cv * 8, pack8(f));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) nhwc_bf16_to_nchw_f32_kernel(View src, float* __restrict__ dst,
+                                                                          int c_dst) {
+  const int CV = (c_dst + 7) >> 3;
+  const long long hw = 1LL * src.h * src.w;
+  const long long total = 1LL * src.n * hw * CV;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    long long p = i % hw;
+    long long t = i / hw;
+    int cv = static_cast<int>(t % CV);
+    int n = static_cast<int>(t / CV);
+    int h = static_cast<int>(p / src.w), w = static_cast<int>(p % src.w);
+    float f[8];
+    unpack8(ldg16(src.p + voff(src, n, h, w) + cv * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cv * 8 + j;
+      if (c < c_dst) dst[(1LL * n * c_dst + c) * hw + p] = f[j];
+    }
+  }
+}
+
+// dst channel k = ci*9 + r*3 + s  <-  x[n, ci, h+r-1, w+s-1]
+__global__ void __launch_bounds__(kThreads) im2col3x3_kernel(const float* __restrict__ src, int c_src, View dst) {
+  const int CV = dst.c >> 3;
+  const long long hw = 1LL * dst.h * dst.w;
+  const long long total = 1LL * dst.n * hw * CV;
+  const int kmax = c_src * 9;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    long long p = i % hw;
+    long long t = i / hw;
+    int cv = static_cast<int>(t % CV);
+    int n = static_cast<int>(t / CV);
+    int h = static_cast<int>(p / dst.w), w = static_cast<int>(p % dst.w);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int k = cv * 8 + j;
+      float v = 0.f;
+      if (k < kmax) {
+        int ci = k / 9, tap = k % 9;
+        int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < dst.h && ww >= 0 && ww < dst.w) v = __ldg(src + (1LL * n * c_src + ci) * hw + 1LL * hh * dst.w + ww);
+      }
+      f[j] = v;
+    }
+    stg16(dst.p + voff(dst, n, h, w) + cv * 8, pack8(f));
+  }
+}
+
+// dst[co][tap][ci] (bf16) <- w[co][ci][tap] (fp32 OIHW); taps==1: dst[co][k] <- w[co][k], k < cin*9
+__global__ void pack_w_fprop_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad,
+                                    int cin_pad, __nv_bfloat16* __restrict__ dst) {
+  const long long total = 1LL * cout_pad * taps * cin_pad;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int ci = static_cast<int>(i % cin_pad);
+    long long t = i / cin_pad;
+    int tap = static_cast<int>(t % taps);
+    int co = static_cast<int>(t / taps);
+    float v = 0.f;
+    if (co < cout) {
+      if (taps == 9) {
+        if (ci < cin) v = w[(1LL * co * cin + ci) * 9 + tap];
+      } else {
+        if (ci < cin * 9) v = w[1LL * co * cin * 9 + ci];
+      }
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dst[ci][tap'][co] (bf16) <- w[co][ci][8 - tap'] : the 180-degree rotated, in/out-transposed filter
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int cout_pad, int cin_pad,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const long long total = 1LL * cin_pad * 9 * cout_pad;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int co = static_cast<int>(i % cout_pad);
+    long long t = i / cout_pad;
+    int tap = static_cast<int>(t % 9);
+    int ci = static_cast<int>(t / 9);
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[(1LL * co * cin + ci) * 9 + (8 - tap)];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) zero_view_kernel(View v) {
+  const int CV = v.c >> 3;
+  const long long total = 1LL * v.n * v.h * v.w * CV;
+  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+    int cv = static_cast<int>(i % CV);
+    long long pix = i / CV;
+    int w = static_cast<int>(pix % v.w);
+    long long t = pix / v.w;
+    int h = static_cast<int>(t % v.h);
+    int n = static_cast<int>(t / v.h);
+    stg16(v.p + voff(v, n, h, w) + cv * 8, make_uint4(0, 0, 0, 0));
+  }
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" int cvb_nchw_f32_to_nhwc_bf16(const float* src, int c_src, cvb_view dst, void* stream) {
+  int rc = check_view(dst, "nchw_to_nhwc.dst");
+  if (rc) return rc;
+  CVB_REQUIRE(src && c_src > 0 && c_src <= dst.c, CVB_ERR_INVALID_ARG, "nchw_to_nhwc: bad source (c_src=%d, dst.c=%d)",
+              c_src, dst.c);
+  long long total = 1LL * dst.n * dst.h * dst.w * (dst.c / 8);
+  nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, c_src, to_dev(dst));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_nhwc_bf16_to_nchw_f32(cvb_view src, float* dst, int c_dst, void* stream) {
+  int rc = check_view(src, "nhwc_to_nchw.src");
+  if (rc) return rc;
+  CVB_REQUIRE(dst && c_dst > 0 && c_dst <= src.c, CVB_ERR_INVALID_ARG, "nhwc_to_nchw: bad destination (c_dst=%d, src.c=%d)",
+              c_dst, src.c);
+  long long total = 1LL * src.n * src.h * src.w * ((c_dst + 7) / 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      to_dev(src), dst, c_dst);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_im2col3x3_nchw_f32(const float* src, int c_src, cvb_view dst, void* stream) {
+  int rc = check_view(dst, "im2col.dst");
+  if (rc) return rc;
+  CVB_REQUIRE(src && c_src > 0 && c_src * 9 <= dst.c, CVB_ERR_INVALID_ARG,
+              "im2col3x3: 9*c_src=%d does not fit the %d destination channels", c_src * 9, dst.c);
+  long long total = 1LL * dst.n * dst.h * dst.w * (dst.c / 8);
+  im2col3x3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, c_src,
+                                                                                                  to_dev(dst));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_pack_weights_fprop(const float* w, int cout, int cin, int taps, int cout_pad, int cin_pad,
+                                      void* dst, void* stream) {
+  CVB_REQUIRE(w && dst, CVB_ERR_INVALID_ARG, "pack_weights_fprop: null pointer");
+  CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "pack_weights_fprop: taps must be 9 or 1");
+  CVB_REQUIRE(cout > 0 && cin > 0 && cout_pad >= cout && cin_pad >= (taps == 9 ? cin : cin * 9), CVB_ERR_INVALID_ARG,
+              "pack_weights_fprop: padded sizes too small");
+  long long total = 1LL * cout_pad * taps * cin_pad;
+  pack_w_fprop_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, taps, cout_pad, cin_pad, static_cast<__nv_bfloat16*>(dst));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_pack_weights_dgrad(const float* w, int cout, int cin, int cout_pad, int cin_pad, void* dst,
+                                      void* stream) {
+  CVB_REQUIRE(w && dst, CVB_ERR_INVALID_ARG, "pack_weights_dgrad: null pointer");
+  CVB_REQUIRE(cout > 0 && cin > 0 && cout_pad >= cout && cin_pad >= cin, CVB_ERR_INVALID_ARG,
+              "pack_weights_dgrad: padded sizes too small");
+  long long total = 1LL * cin_pad * 9 * cout_pad;
+  pack_w_dgrad_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, cout_pad, cin_pad, static_cast<__nv_bfloat16*>(dst));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_zero_view(cvb_view v, void* stream) {
+  int rc = check_view(v, "zero_view");
+  if (rc) return rc;
+  long long total = 1LL * v.n * v.h * v.w * (v.c / 8);
+  zero_view_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(v));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}

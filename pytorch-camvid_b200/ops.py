@@ -1,0 +1,253 @@
+"""Thin operator layer over the C ABI: torch tensors in, kernels enqueued on torch's current CUDA stream.
+
+Activations are torch bf16 tensors of logical shape [N, H, W, C] with stride(3) == 1 (NHWC); channel slices and row
+windows of a larger buffer are passed as strided views, no copies. Nothing here computes on the host or falls back to
+PyTorch kernels: every function ends in one call into libcamvid_b200.so and raises RuntimeError on failure.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvEpilogue, View
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def view(t):
+    """cvb_view of an NHWC bf16 tensor (possibly a strided slice)."""
+    if t is None:
+        return View(None, 0, 0, 0, 0, 0, 0, 0)
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4):
+        raise RuntimeError(f"expected a CUDA bf16 [N,H,W,C] tensor, got {t.dtype} {tuple(t.shape)} on {t.device}")
+    if t.stride(3) != 1:
+        raise RuntimeError("NHWC view must have channel stride 1")
+    n, h, w, c = t.shape
+    return View(t.data_ptr(), n, h, w, c, t.stride(0), t.stride(1), t.stride(2))
+
+
+def _f32(t, name):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous CUDA fp32 tensor")
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def sm_count():
+    return _lib.load().cvb_sm_count()
+
+
+def stat_rows():
+    return _lib.load().cvb_conv_stat_rows()
+
+
+# ---------------------------------------------------------------- layout
+def nchw_to_nhwc(src, dst):
+    """src fp32 [N,C,H,W] contiguous -> dst NHWC bf16 view (extra channels zeroed)."""
+    _f32(src, "nchw_to_nhwc.src")
+    _lib.check(_lib.load().cvb_nchw_f32_to_nhwc_bf16(_ptr(src), src.shape[1], view(dst), _stream()), "nchw_to_nhwc")
+    return dst
+
+
+def nhwc_to_nchw(src, dst):
+    """src NHWC bf16 view -> dst fp32 [N,C,H,W] contiguous (first C channels)."""
+    _f32(dst, "nhwc_to_nchw.dst")
+    _lib.check(_lib.load().cvb_nhwc_bf16_to_nchw_f32(view(src), _ptr(dst), dst.shape[1], _stream()), "nhwc_to_nchw")
+    return dst
+
+
+def im2col3x3(src, dst):
+    _f32(src, "im2col3x3.src")
+    _lib.check(_lib.load().cvb_im2col3x3_nchw_f32(_ptr(src), src.shape[1], view(dst), _stream()), "im2col3x3")
+    return dst
+
+
+def zero_view(t):
+    _lib.check(_lib.load().cvb_zero_view(view(t), _stream()), "zero_view")
+    return t
+
+
+# ---------------------------------------------------------------- convolution
+def pack_weights_fprop(w, taps, cout_pad, cin_pad, out=None):
+    """OIHW fp32 -> bf16 [cout_pad, taps*cin_pad] GEMM-B matrix."""
+    _f32(w, "pack_weights_fprop.w")
+    cout, cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty(cout_pad, taps * cin_pad, dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.load().cvb_pack_weights_fprop(_ptr(w), cout, cin, taps, cout_pad, cin_pad, _ptr(out), _stream()),
+               "pack_weights_fprop")
+    return out
+
+
+def pack_weights_dgrad(w, cout_pad, cin_pad, out=None):
+    """OIHW fp32 -> bf16 [cin_pad, 9*cout_pad] rotated/transposed GEMM-B matrix of the data-gradient conv."""
+    _f32(w, "pack_weights_dgrad.w")
+    cout, cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty(cin_pad, 9 * cout_pad, dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.load().cvb_pack_weights_dgrad(_ptr(w), cout, cin, cout_pad, cin_pad, _ptr(out), _stream()),
+               "pack_weights_dgrad")
+    return out
+
+
+def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False):
+    """y = conv(x, wpack). Optional epilogues: BN statistics partials (train) or folded scale/shift(+ReLU) (eval)."""
+    ep = ConvEpilogue(stat_partials.data_ptr() if stat_partials is not None else None,
+                      scale.data_ptr() if scale is not None else None,
+                      shift.data_ptr() if shift is not None else None, 1 if relu else 0)
+    if stat_partials is not None:
+        _f32(stat_partials, "conv3x3.stat_partials")
+        if stat_partials.numel() < stat_rows() * 2 * y.shape[3]:
+            raise RuntimeError("conv3x3: stat_partials too small")
+    _lib.check(_lib.load().cvb_conv3x3_fprop(view(x), _ptr(wpack), taps, view(y), ctypes.byref(ep), _stream()),
+               "conv3x3_fprop")
+    return y
+
+
+def conv3x3_wgrad_workspace_bytes(x, dy, taps=9):
+    r = _lib.load().cvb_conv3x3_wgrad_workspace_bytes(view(x), view(dy), taps)
+    if r < 0:
+        _lib.check(int(r), "conv3x3_wgrad_workspace_bytes")
+    return int(r)
+
+
+def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None):
+    """dw (fp32 OIHW [cout,cin,3,3], overwritten) = weight gradient from activations x and output gradient dy."""
+    _f32(dw, "conv3x3_wgrad.dw")
+    cout, cin = dw.shape[0], dw.shape[1]
+    need = conv3x3_wgrad_workspace_bytes(x, dy, taps)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.load().cvb_conv3x3_wgrad(view(x), view(dy), taps, _ptr(dw), cout, cin, _ptr(workspace),
+                                             workspace.numel() * workspace.element_size(), _stream()),
+               "conv3x3_wgrad")
+    return dw
+
+
+# ---------------------------------------------------------------- batch norm (+ReLU)
+def bn_stats(y, partials, rows):
+    _lib.check(_lib.load().cvb_bn_stats(view(y), _ptr(partials), rows, _stream()), "bn_stats")
+    return partials
+
+
+def bn_finalize(partials, rows, c, c_pad, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps,
+                mean, invstd, scale, shift):
+    _lib.check(_lib.load().cvb_bn_finalize(_ptr(partials), rows, c, c_pad, count, _ptr(gamma), _ptr(beta),
+                                           _ptr(conv_bias), _ptr(running_mean), _ptr(running_var), momentum, eps,
+                                           _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _stream()),
+               "bn_finalize")
+
+
+def bn_relu_apply(y, scale, shift, a):
+    _lib.check(_lib.load().cvb_bn_relu_apply(view(y), _ptr(scale), _ptr(shift), view(a), _stream()), "bn_relu_apply")
+    return a
+
+
+def bn_relu_bwd_reduce(da, y, scale, shift, partials, rows):
+    _lib.check(_lib.load().cvb_bn_relu_bwd_reduce(view(da), view(y), _ptr(scale), _ptr(shift), _ptr(partials), rows,
+                                                  _stream()), "bn_relu_bwd_reduce")
+
+
+def bn_bwd_finalize(partials, rows, c, c_pad, count, gamma, mean, invstd, dgamma, dbeta, coef):
+    _lib.check(_lib.load().cvb_bn_bwd_finalize(_ptr(partials), rows, c, c_pad, count, _ptr(gamma), _ptr(mean),
+                                               _ptr(invstd), _ptr(dgamma), _ptr(dbeta), _ptr(coef), _stream()),
+               "bn_bwd_finalize")
+
+
+def bn_relu_bwd_apply(da, y, scale, shift, coef, dy):
+    _lib.check(_lib.load().cvb_bn_relu_bwd_apply(view(da), view(y), _ptr(scale), _ptr(shift), _ptr(coef), view(dy),
+                                                 _stream()), "bn_relu_bwd_apply")
+    return dy
+
+
+# ---------------------------------------------------------------- pooling
+def maxpool2x2(x, out, code=None):
+    _lib.check(_lib.load().cvb_maxpool2x2_fwd(view(x), view(out), _ptr(code), _stream()), "maxpool2x2_fwd")
+    return out
+
+
+def bn_relu_maxpool2x2(y, scale, shift, a, out, code=None):
+    _lib.check(_lib.load().cvb_bn_relu_maxpool2x2_fwd(view(y), _ptr(scale), _ptr(shift), view(a), view(out),
+                                                      _ptr(code), _stream()), "bn_relu_maxpool2x2_fwd")
+    return out
+
+
+def maxpool2x2_bwd(dout, dx, code=None, x=None, accumulate=False):
+    _lib.check(_lib.load().cvb_maxpool2x2_bwd(view(dout), _ptr(code), view(x), view(dx), 1 if accumulate else 0,
+                                              _stream()), "maxpool2x2_bwd")
+    return dx
+
+
+def maxunpool2x2(x, code, out):
+    _lib.check(_lib.load().cvb_maxunpool2x2_fwd(view(x), _ptr(code), view(out), _stream()), "maxunpool2x2_fwd")
+    return out
+
+
+def maxunpool2x2_bwd(dout, code, dx):
+    _lib.check(_lib.load().cvb_maxunpool2x2_bwd(view(dout), _ptr(code), view(dx), _stream()), "maxunpool2x2_bwd")
+    return dx
+
+
+def pool_code_to_index(code, w_in):
+    """uint8 codes [N,Ho,Wo,C] -> torch-style int64 indices [N,C,Ho,Wo] (h*W_in + w per plane)."""
+    n, ho, wo, c = code.shape
+    idx = torch.empty(n, c, ho, wo, dtype=torch.int64, device=code.device)
+    _lib.check(_lib.load().cvb_pool_code_to_index(_ptr(code), n, ho, wo, c, w_in, _ptr(idx), _stream()),
+               "pool_code_to_index")
+    return idx
+
+
+# ---------------------------------------------------------------- upsample
+def bilinear2x(x, out):
+    _lib.check(_lib.load().cvb_bilinear2x_fwd(view(x), view(out), _stream()), "bilinear2x_fwd")
+    return out
+
+
+def bilinear2x_bwd(dout, dx):
+    _lib.check(_lib.load().cvb_bilinear2x_bwd(view(dout), view(dx), _stream()), "bilinear2x_bwd")
+    return dx
+
+
+# ---------------------------------------------------------------- loss / metric
+def softmax_ce_nchw(logits, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
+    _f32(logits, "softmax_ce.logits")
+    n, c, h, w = logits.shape
+    _lib.check(_lib.load().cvb_softmax_ce_nchw_f32(_ptr(logits), _ptr(target), n, c, h, w, ignore_index,
+                                                   _ptr(loss_sum_count), _ptr(dlogits), grad_scale,
+                                                   _ptr(grad_scale_dev), _stream()), "softmax_ce_nchw_f32")
+
+
+def softmax_ce_nhwc(logits, c, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
+    _lib.check(_lib.load().cvb_softmax_ce_nhwc_bf16(view(logits), c, _ptr(target), ignore_index, _ptr(loss_sum_count),
+                                                    view(dlogits), grad_scale, _ptr(grad_scale_dev), _stream()),
+               "softmax_ce_nhwc_bf16")
+
+
+def confusion_matrix(pred, gt, c, cm):
+    _lib.check(_lib.load().cvb_confusion_matrix(_ptr(pred), _ptr(gt), pred.numel(), c, _ptr(cm), _stream()),
+               "confusion_matrix")
+    return cm
+
+
+def argmax_confusion_nchw(logits, gt, cm, pred=None):
+    _f32(logits, "argmax_confusion.logits")
+    n, c, h, w = logits.shape
+    _lib.check(_lib.load().cvb_argmax_confusion_nchw_f32(_ptr(logits), _ptr(gt), n, c, h, w, _ptr(pred), _ptr(cm),
+                                                         _stream()), "argmax_confusion_nchw_f32")
+    return cm
+
+
+def argmax_confusion_nhwc(logits, c, gt, cm, pred=None):
+    _lib.check(_lib.load().cvb_argmax_confusion_nhwc_bf16(view(logits), c, _ptr(gt), _ptr(pred), _ptr(cm), _stream()),
+               "argmax_confusion_nhwc_bf16")
+    return cm

@@ -1,0 +1,342 @@
+"""Op-level parity of the CUDA kernels (through the C ABI) against the ATen ops the reference calls.
+
+Oracle = torch fp32 ops on the same (bf16-representable) inputs, TF32 disabled. Integer / index results must be
+bit-exact; floating-point results are compared norm-wise with the tolerance stated in each test.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import bf16_round, rel_err, to_nchw_f32, to_nhwc_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    import camvid_b200  # noqa: F401
+    from camvid_b200 import ops as _ops
+    return _ops
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return bf16_round(torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+# ------------------------------------------------------------------------------------------- layout
+def test_layout_roundtrip(ops, cuda):
+    x = _rand((2, 3, 13, 17), cuda, 0)
+    dst = torch.full((2, 13, 17, 64), 7.0, dtype=torch.bfloat16, device=cuda)
+    ops.nchw_to_nhwc(x, dst)
+    assert torch.equal(dst[..., :3].float(), x.permute(0, 2, 3, 1))
+    assert torch.count_nonzero(dst[..., 3:]) == 0
+    back = torch.empty(2, 3, 13, 17, device=cuda)
+    ops.nhwc_to_nchw(dst, back)
+    assert torch.equal(back, x)
+
+
+def test_im2col(ops, cuda):
+    x = _rand((2, 3, 9, 11), cuda, 1)
+    dst = torch.empty(2, 9, 11, 64, dtype=torch.bfloat16, device=cuda)
+    ops.im2col3x3(x, dst)
+    ref = F.unfold(x, 3, padding=1).view(2, 27, 9, 11).permute(0, 2, 3, 1)  # k = ci*9 + r*3 + s
+    assert torch.equal(dst[..., :27].float(), ref)
+    assert torch.count_nonzero(dst[..., 27:]) == 0
+
+
+# ------------------------------------------------------------------------------------------- convolution
+CONV_CASES = [
+    # n, h, w, cin, cout
+    (2, 16, 24, 64, 64),
+    (1, 45, 60, 128, 256),
+    (3, 22, 30, 64, 512),
+    (2, 11, 15, 192, 64),
+    (1, 8, 136, 64, 128),
+    (16, 5, 7, 128, 128),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_CASES)
+def test_conv_fprop(ops, cuda, n, h, w, cin, cout):
+    x = _rand((n, cin, h, w), cuda, 2)
+    wt = _rand((cout, cin, 3, 3), cuda, 3, scale=(cin * 9) ** -0.5)
+    ref = F.conv2d(x, wt, padding=1)
+    xs = to_nhwc_bf16(x)
+    wp = ops.pack_weights_fprop(wt, 9, cout, cin)
+    y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+    parts = torch.full((ops.stat_rows(), 2, cout), float("nan"), device=cuda)
+    ops.conv3x3(xs, wp, y, stat_partials=parts)
+    torch.cuda.synchronize()
+    got = to_nchw_f32(y)
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 4e-3  # bf16 output rounding only (operands are exact in bf16, fp32 accumulate)
+    # fused BatchNorm statistics: per-channel sum and sum of squares of the fp32 accumulators
+    s = parts.sum(0)
+    assert rel_err(s[0], ref.sum((0, 2, 3))) < 2e-3
+    assert rel_err(s[1], (ref * ref).sum((0, 2, 3))) < 2e-3
+
+
+def test_conv_fprop_eval_epilogue_and_strided_output(ops, cuda):
+    n, h, w, cin, cout = 2, 12, 20, 64, 64
+    x = _rand((n, cin, h, w), cuda, 4)
+    wt = _rand((cout, cin, 3, 3), cuda, 5, scale=(cin * 9) ** -0.5)
+    scale = torch.rand(cout, device=cuda) + 0.5
+    shift = torch.randn(cout, device=cuda) * 0.3
+    ref = F.relu(F.conv2d(x, wt, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    big = torch.full((n, h + 1, w, 192), 3.0, dtype=torch.bfloat16, device=cuda)
+    y = big[:, :h, :, 64:128]  # channel slice of a concat buffer with one extra (pad) row
+    ops.conv3x3(to_nhwc_bf16(x), ops.pack_weights_fprop(wt, 9, cout, cin), y, scale=scale, shift=shift, relu=True)
+    assert rel_err(to_nchw_f32(y), ref) < 4e-3
+    assert (big[:, h] == 3).all() and (big[..., :64] == 3).all() and (big[..., 128:] == 3).all()
+
+
+def test_conv_first_layer_im2col(ops, cuda):
+    n, h, w, cin, cout = 2, 20, 28, 3, 64
+    x = _rand((n, cin, h, w), cuda, 6)
+    wt = _rand((cout, cin, 3, 3), cuda, 7, scale=27 ** -0.5)
+    ref = F.conv2d(x, wt, padding=1)
+    cols = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    ops.im2col3x3(x, cols)
+    wp = ops.pack_weights_fprop(wt, 1, 64, 64)
+    y = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    ops.conv3x3(cols, wp, y, taps=1)
+    assert rel_err(to_nchw_f32(y), ref) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_CASES[:4])
+def test_conv_dgrad(ops, cuda, n, h, w, cin, cout):
+    x = _rand((n, cin, h, w), cuda, 8).requires_grad_(True)
+    wt = _rand((cout, cin, 3, 3), cuda, 9, scale=(cin * 9) ** -0.5)
+    dy = _rand((n, cout, h, w), cuda, 10)
+    (ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), x, dy)
+    wp = ops.pack_weights_dgrad(wt, cout, cin)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=cuda)
+    ops.conv3x3(to_nhwc_bf16(dy), wp, dx)
+    assert rel_err(to_nchw_f32(dx), ref) < 4e-3
+
+
+WGRAD_CASES = [
+    (2, 16, 24, 64, 64),
+    (2, 23, 31, 128, 64),
+    (2, 16, 16, 64, 128),
+    (1, 45, 60, 128, 256),
+    (3, 22, 30, 256, 128),
+    (2, 11, 15, 512, 512),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", WGRAD_CASES)
+def test_conv_wgrad(ops, cuda, n, h, w, cin, cout):
+    x = _rand((n, cin, h, w), cuda, 11)
+    wt = _rand((cout, cin, 3, 3), cuda, 12).requires_grad_(True)
+    dy = _rand((n, cout, h, w), cuda, 13)
+    (ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
+    dw = torch.full((cout, cin, 3, 3), float("nan"), device=cuda)
+    ops.conv3x3_wgrad(to_nhwc_bf16(x), to_nhwc_bf16(dy), dw)
+    assert torch.isfinite(dw).all()
+    assert rel_err(dw, ref) < 1e-4  # fp32 accumulate of exact bf16 products, fp32 output
+
+
+def test_conv_wgrad_first_layer_and_padded_cout(ops, cuda):
+    n, h, w = 2, 20, 28
+    x = _rand((n, 3, h, w), cuda, 14)
+    wt = _rand((64, 3, 3, 3), cuda, 15).requires_grad_(True)
+    dy = _rand((n, 64, h, w), cuda, 16)
+    (ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
+    cols = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    ops.im2col3x3(x, cols)
+    dw = torch.empty(64, 3, 3, 3, device=cuda)
+    ops.conv3x3_wgrad(cols, to_nhwc_bf16(dy), dw, taps=1)
+    assert rel_err(dw, ref) < 1e-4
+    # last layer: cout = 12 padded to 64 channels of dy (pad channels zero)
+    x2 = _rand((n, 64, h, w), cuda, 17)
+    w2 = _rand((12, 64, 3, 3), cuda, 18).requires_grad_(True)
+    dy2 = _rand((n, 12, h, w), cuda, 19)
+    (ref2,) = torch.autograd.grad(F.conv2d(x2, w2, padding=1), w2, dy2)
+    dyp = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    dyp[..., :12] = to_nhwc_bf16(dy2)
+    dw2 = torch.empty(12, 64, 3, 3, device=cuda)
+    ops.conv3x3_wgrad(to_nhwc_bf16(x2), dyp, dw2)
+    assert rel_err(dw2, ref2) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize("n,h,w,c,creal", [(2, 9, 13, 64, 64), (3, 8, 8, 256, 256), (2, 10, 6, 64, 12), (1, 7, 5, 1024, 1024)])
+def test_bn_relu_train(ops, cuda, n, h, w, c, creal):
+    torch.manual_seed(20)
+    y = bf16_round(torch.randn(n, c, h, w) * 1.7 + 0.4).to(cuda)
+    y[:, creal:] = 0
+    gamma = (torch.rand(creal) + 0.5).to(cuda)
+    beta = (torch.randn(creal) * 0.2).to(cuda)
+    bias = (torch.randn(creal) * 0.1).to(cuda)
+    rm = torch.randn(creal).to(cuda)
+    rv = (torch.rand(creal) + 0.5).to(cuda)
+    da = bf16_round(torch.randn(n, c, h, w)).to(cuda)
+    # oracle: F.batch_norm (train) + relu on (y + bias); the kernels drop the bias and add it back to running_mean
+    yr = (y[:, :creal] + bias.view(1, -1, 1, 1)).clone().requires_grad_(True)
+    g_ = gamma.clone().requires_grad_(True)
+    b_ = beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a_ref = F.relu(F.batch_norm(yr, rm_ref, rv_ref, g_, b_, True, 0.1, 1e-5))
+    dy_ref, dg_ref, db_ref = torch.autograd.grad(a_ref, (yr, g_, b_), da[:, :creal])
+
+    ys, das = to_nhwc_bf16(y), to_nhwc_bf16(da)
+    rows = 37
+    parts = torch.empty(rows, 2, c, device=cuda)
+    ops.bn_stats(ys, parts, rows)
+    mean, invstd, scale, shift = (torch.empty(c, device=cuda) for _ in range(4))
+    count = n * h * w
+    ops.bn_finalize(parts, rows, creal, c, count, gamma, beta, bias, rm, rv, 0.1, 1e-5, mean, invstd, scale, shift)
+    a = torch.empty_like(ys)
+    ops.bn_relu_apply(ys, scale, shift, a)
+    assert rel_err(to_nchw_f32(a)[:, :creal], a_ref) < 4e-3
+    assert torch.count_nonzero(a[..., creal:]) == 0
+    assert torch.allclose(rm, rm_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-6)
+    # backward
+    ops.bn_relu_bwd_reduce(das, ys, scale, shift, parts, rows)
+    dgamma, dbeta = torch.empty(creal, device=cuda), torch.empty(creal, device=cuda)
+    coef = torch.empty(3, c, device=cuda)
+    ops.bn_bwd_finalize(parts, rows, creal, c, count, gamma, mean, invstd, dgamma, dbeta, coef)
+    dy = torch.empty_like(ys)
+    ops.bn_relu_bwd_apply(das, ys, scale, shift, coef, dy)
+    assert rel_err(dgamma, dg_ref) < 1e-3
+    assert rel_err(dbeta, db_ref) < 1e-3
+    assert rel_err(to_nchw_f32(dy)[:, :creal], dy_ref) < 5e-3
+    assert torch.count_nonzero(dy[..., creal:]) == 0
+
+
+# ------------------------------------------------------------------------------------------- pooling
+@pytest.mark.parametrize("n,h,w,c", [(2, 8, 12, 64), (1, 45, 61, 64), (3, 11, 15, 128)])
+def test_maxpool_indices_bit_exact(ops, cuda, n, h, w, c):
+    torch.manual_seed(21)
+    x = F.relu(bf16_round(torch.randn(n, c, h, w))).to(cuda)  # ~half zeros -> plenty of ties
+    x[0, 0, 0, 1] = float("nan")
+    x[0, 1, 1, 0] = float("nan")
+    x[0, 1, 1, 1] = float("nan")
+    ref, idx_ref = F.max_pool2d(x, 2, return_indices=True)
+    xs = to_nhwc_bf16(x)
+    out = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=cuda)
+    code = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=cuda)
+    ops.maxpool2x2(xs, out, code)
+    got = to_nchw_f32(out)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    assert torch.equal(ops.pool_code_to_index(code, w), idx_ref)
+    # backward = scatter; must equal torch's max_pool2d backward exactly (values are copied, not computed)
+    dout = bf16_round(torch.randn(n, c, h // 2, w // 2)).to(cuda)
+    dx_ref = F.max_unpool2d(dout, idx_ref, 2, output_size=x.shape)  # aten's max_pool2d backward is this scatter
+    dx = torch.full((n, h, w, c), 5.0, dtype=torch.bfloat16, device=cuda)
+    ops.maxpool2x2_bwd(to_nhwc_bf16(dout), dx, code=code)
+    assert torch.equal(to_nchw_f32(dx), dx_ref)
+    # recompute-from-input variant and accumulate variant
+    dx2 = torch.ones(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+    ops.maxpool2x2_bwd(to_nhwc_bf16(dout), dx2, x=xs, accumulate=True)
+    assert torch.equal(to_nchw_f32(dx2), bf16_round(dx_ref + 1.0))
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 8, 12, 64), (1, 45, 61, 64)])
+def test_maxunpool_bit_exact(ops, cuda, n, h, w, c):
+    torch.manual_seed(22)
+    x = F.relu(bf16_round(torch.randn(n, c, h, w))).to(cuda)
+    pooled, idx = F.max_pool2d(x, 2, return_indices=True)
+    v = bf16_round(torch.randn_like(pooled))
+    ref = F.max_unpool2d(v, idx, 2, output_size=x.shape)
+    code = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=cuda)
+    tmp = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=cuda)
+    ops.maxpool2x2(to_nhwc_bf16(x), tmp, code)
+    out = torch.full((n, h, w, c), 9.0, dtype=torch.bfloat16, device=cuda)
+    ops.maxunpool2x2(to_nhwc_bf16(v), code, out)
+    assert torch.equal(to_nchw_f32(out), ref)
+    dout = bf16_round(torch.randn(n, c, h, w)).to(cuda)
+    vr = v.clone().requires_grad_(True)
+    (dv_ref,) = torch.autograd.grad(F.max_unpool2d(vr, idx, 2, output_size=x.shape), vr, dout)
+    dv = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=cuda)
+    ops.maxunpool2x2_bwd(to_nhwc_bf16(dout), code, dv)
+    assert torch.equal(to_nchw_f32(dv), dv_ref)
+
+
+def test_bn_relu_maxpool_fused(ops, cuda):
+    n, h, w, c = 2, 9, 14, 64
+    torch.manual_seed(23)
+    y = to_nhwc_bf16(bf16_round(torch.randn(n, c, h, w)).to(cuda))
+    scale = (torch.rand(c) + 0.5).to(cuda)
+    shift = (torch.randn(c) * 0.3).to(cuda)
+    a_ref = torch.empty_like(y)
+    ops.bn_relu_apply(y, scale, shift, a_ref)
+    p_ref = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=cuda)
+    c_ref = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=cuda)
+    ops.maxpool2x2(a_ref, p_ref, c_ref)
+    a, p, cd = torch.empty_like(a_ref), torch.empty_like(p_ref), torch.empty_like(c_ref)
+    ops.bn_relu_maxpool2x2(y, scale, shift, a, p, cd)
+    assert torch.equal(a, a_ref) and torch.equal(p, p_ref) and torch.equal(cd, c_ref)
+
+
+# ------------------------------------------------------------------------------------------- upsample
+@pytest.mark.parametrize("n,h,w,c", [(2, 5, 7, 64), (1, 22, 30, 128), (1, 1, 3, 64)])
+def test_bilinear2x(ops, cuda, n, h, w, c):
+    torch.manual_seed(24)
+    x = bf16_round(torch.randn(n, c, h, w)).to(cuda).requires_grad_(True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=cuda)
+    ops.bilinear2x(to_nhwc_bf16(x.detach()), out)
+    assert rel_err(to_nchw_f32(out), ref) < 4e-3
+    dout = bf16_round(torch.randn(n, c, 2 * h, 2 * w)).to(cuda)
+    (dx_ref,) = torch.autograd.grad(ref, x, dout)
+    dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+    ops.bilinear2x_bwd(to_nhwc_bf16(dout), dx)
+    assert rel_err(to_nchw_f32(dx), dx_ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------- loss / metric
+@pytest.mark.parametrize("ignore", [-100, 11])
+def test_softmax_ce(ops, cuda, ignore):
+    torch.manual_seed(25)
+    n, c, h, w = 3, 12, 17, 23
+    logits = F.relu(torch.randn(n, c, h, w) * 2).to(cuda).requires_grad_(True)
+    target = torch.randint(0, c, (n, h, w)).to(cuda)
+    ref = F.cross_entropy(logits, target, ignore_index=ignore)
+    (dref,) = torch.autograd.grad(ref, logits)
+    acc = torch.zeros(2, dtype=torch.float64, device=cuda)
+    dl = torch.empty_like(logits)
+    cnt = (target != ignore).sum()
+    inv = (1.0 / cnt.float()).reshape(1)
+    ops.softmax_ce_nchw(logits.detach(), target, ignore, acc, dl, 1.0, inv)
+    assert acc[1].item() == cnt.item()
+    assert abs(acc[0].item() / acc[1].item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert rel_err(dl, dref) < 1e-5
+    # NHWC bf16 variant (model-internal logits, 64-channel padded gradient)
+    lg = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    lg[..., :c] = to_nhwc_bf16(logits.detach())
+    lq = to_nchw_f32(lg[..., :c]).requires_grad_(True)
+    ref2 = F.cross_entropy(lq, target, ignore_index=ignore)
+    (dref2,) = torch.autograd.grad(ref2, lq)
+    acc.zero_()
+    dl2 = torch.full((n, h, w, 64), 1.0, dtype=torch.bfloat16, device=cuda)
+    ops.softmax_ce_nhwc(lg, c, target, ignore, acc, dl2, 1.0, inv)
+    assert abs(acc[0].item() / acc[1].item() - ref2.item()) < 1e-5 * max(1.0, abs(ref2.item()))
+    assert rel_err(to_nchw_f32(dl2[..., :c]), dref2) < 4e-3
+    assert torch.count_nonzero(dl2[..., c:]) == 0
+
+
+def test_confusion_matrix_bit_exact(ops, cuda):
+    torch.manual_seed(26)
+    n, c, h, w = 4, 12, 33, 47
+    logits = F.relu(torch.randn(n, c, h, w)).to(cuda)  # post-ReLU: argmax ties at 0 resolve to the first index
+    gt = torch.randint(0, c, (n, h, w)).to(cuda)
+    pred_ref = logits.argmax(1)
+    cm_ref = torch.zeros(c, c, dtype=torch.int64, device=cuda)
+    cm_ref.view(-1).index_add_(0, (gt * c + pred_ref).view(-1), torch.ones(gt.numel(), dtype=torch.int64, device=cuda))
+    cm = torch.zeros(c, c, dtype=torch.int64, device=cuda)
+    pred = torch.empty(n, h, w, dtype=torch.int64, device=cuda)
+    ops.argmax_confusion_nchw(logits, gt, cm, pred)
+    assert torch.equal(pred, pred_ref) and torch.equal(cm, cm_ref)
+    cm.zero_()
+    ops.confusion_matrix(pred_ref, gt, c, cm)
+    assert torch.equal(cm, cm_ref)
+    cm.zero_()
+    lg = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    lg[..., :c] = to_nhwc_bf16(logits)
+    pred2 = torch.empty_like(pred)
+    ops.argmax_confusion_nhwc(lg, c, gt, cm, pred2)
+    assert torch.equal(pred2, to_nchw_f32(lg[..., :c]).argmax(1))
