@@ -183,10 +183,14 @@ CVB_API int cvb_softmax_ce_nhwc_bf16(cvb_view logits, int c, const int64_t* targ
 
 /* ---------------------------------------------------------------------------------------------------------------
  * preds.argmax(dim=1) + confusion matrix (train.py:191-194, utils.py:162-228, legacy/metrics.py:22-30).
- * cm: int64 [c][c], rows = ground truth, cols = prediction, ACCUMULATED into (caller zeroes). Labels outside
- * [0,c) are skipped (sklearn `labels=range(C)` semantics).
+ * cm: int64 [c][c], rows = ground truth, cols = prediction, ACCUMULATED into (caller zeroes).
+ * cvb_confusion_matrix: pixels with gt == ignore_label are dropped (utils.py:178); with clamp_oob == 0 a pair with
+ * either label outside [0,c) is dropped (sklearn `labels=range(C)`, legacy/metrics.py:29); with clamp_oob != 0 such
+ * labels are counted in class c-1 (lets the caller keep an explicit out-of-range bucket, used to reproduce
+ * np.histogram's per-array range handling in utils.py:183-187).
  * ------------------------------------------------------------------------------------------------------------- */
-CVB_API int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c, int64_t* cm, void* stream);
+CVB_API int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c, int64_t ignore_label,
+                                 int clamp_oob, int64_t* cm, void* stream);
 /* Fused: first-max argmax over c channels of NCHW fp32 logits; optionally also writes pred (int64 [n,h,w]). */
 CVB_API int cvb_argmax_confusion_nchw_f32(const float* logits, const int64_t* gt, int n, int c, int h, int w,
                                   int64_t* pred_or_null, int64_t* cm, void* stream);

@@ -61,7 +61,7 @@ SIGNATURES = {
     "cvb_bilinear2x_bwd": (_I, [View, View, _P]),
     "cvb_softmax_ce_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P]),
     "cvb_softmax_ce_nhwc_bf16": (_I, [View, _I, _P, _L, _P, View, _F, _P, _P]),
-    "cvb_confusion_matrix": (_I, [_P, _P, _L, _I, _P, _P]),
+    "cvb_confusion_matrix": (_I, [_P, _P, _L, _I, _L, _I, _P, _P]),
     "cvb_argmax_confusion_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_argmax_confusion_nhwc_bf16": (_I, [View, _I, _P, _P, _P, _P]),
     "cvb_zero_view": (_I, [View, _P]),

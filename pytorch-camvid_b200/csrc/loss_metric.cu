@@ -143,12 +143,17 @@ __device__ __forceinline__ void cm_flush(const unsigned int* hist, int cc, int64
 
 __global__ void __launch_bounds__(kThreads) confmat_kernel(const int64_t* __restrict__ pred,
                                                             const int64_t* __restrict__ gt, long long count, int c,
-                                                            int64_t* cm) {
+                                                            long long ignore_label, int clamp_oob, int64_t* cm) {
   extern __shared__ unsigned int hist[];
   for (int i = threadIdx.x; i < c * c; i += kThreads) hist[i] = 0;
   __syncthreads();
   for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < count; i += 1LL * gridDim.x * kThreads) {
     long long p = pred[i], g = gt[i];
+    if (g == ignore_label) continue;
+    if (clamp_oob) {
+      if (p < 0 || p >= c) p = c - 1;
+      if (g < 0 || g >= c) g = c - 1;
+    }
     if (p >= 0 && p < c && g >= 0 && g < c) atomicAdd(&hist[g * c + p], 1u);
   }
   cm_flush(hist, c * c, cm);
@@ -264,15 +269,15 @@ static int cm_check(int c) {
   return CVB_OK;
 }
 
-extern "C" int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c, int64_t* cm,
-                                    void* stream) {
+extern "C" int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c,
+                                    int64_t ignore_label, int clamp_oob, int64_t* cm, void* stream) {
   CVB_REQUIRE(cm, CVB_ERR_INVALID_ARG, "confusion_matrix: null cm");
   int rc = cm_check(c);
   if (rc) return rc;
   if (count == 0) return CVB_OK;  // empty input: nothing to add (sklearn returns zeros)
   CVB_REQUIRE(pred && gt && count > 0, CVB_ERR_INVALID_ARG, "confusion_matrix: null pointer or negative count");
   confmat_kernel<<<ew_grid(count, kThreads, 4), kThreads, c * c * sizeof(unsigned int),
-                   static_cast<cudaStream_t>(stream)>>>(pred, gt, count, c, cm);
+                   static_cast<cudaStream_t>(stream)>>>(pred, gt, count, c, ignore_label, clamp_oob, cm);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -1,0 +1,446 @@
+"""Execution plans behind the drop-in UNet / SegNet modules.
+
+A plan owns every device buffer one (batch, height, width) configuration needs -- NHWC bf16 activations, raw conv
+outputs, concat buffers written in place by their producers, pooling codes, per-layer BatchNorm vectors, packed bf16
+weights, the wgrad split-K workspace -- and issues the kernel sequence of the forward and backward pass through the
+C ABI (ops.py). Nothing is allocated per step except the flat fp32 gradient buffer handed to autograd.
+
+Reference topology: models/unet.py:35-156 and models/segnet.py:19-119; one "block" is the reference's
+BasicConv2d / BasicConv (conv3x3 pad 1 + BatchNorm2d + ReLU, models/unet.py:5-17, models/segnet.py:5-17).
+"""
+import torch
+
+from . import ops
+from .ops import pad64
+
+
+class Block:
+    """conv3x3(pad 1, bias) + BatchNorm2d + ReLU on NHWC bf16 views."""
+
+    def __init__(self, plan, name, conv, bn, x, a, taps=9):
+        self.plan, self.name, self.conv, self.bn = plan, name, conv, bn
+        self.x, self.a, self.taps = x, a, taps
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        n, h, w, self.cin_pad = x.shape
+        self.cout_pad = a.shape[3]
+        assert a.shape[:3] == x.shape[:3], (name, a.shape, x.shape)
+        assert self.cout_pad == pad64(self.cout) and self.cin_pad % 64 == 0
+        self.count = n * h * w
+        dev = x.device
+        self.y = torch.empty(n, h, w, self.cout_pad, dtype=torch.bfloat16, device=dev)  # conv output, later dy
+        self.vec = torch.zeros(4, self.cout_pad, device=dev)  # mean, invstd, scale, shift
+        self.coef = torch.zeros(3, self.cout_pad, device=dev)
+        self.wf = torch.empty(self.cout_pad, taps * self.cin_pad, dtype=torch.bfloat16, device=dev)
+        self.wd = None if taps == 1 else torch.empty(self.cin_pad, 9 * self.cout_pad, dtype=torch.bfloat16, device=dev)
+        self.wf_version = self.wd_version = None
+        self.ws_bytes = ops.conv3x3_wgrad_workspace_bytes(x, self.y, taps)
+        # offsets into the flat gradient buffer, assigned by the plan
+        self.g_w = self.g_b = self.g_gamma = self.g_beta = None
+
+    # ---- parameters in reference order: conv.weight, conv.bias, bn.weight, bn.bias
+    def params(self):
+        return [self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias]
+
+    def _weight_key(self):
+        w = self.conv.weight
+        return (w.data_ptr(), w._version)
+
+    def _pack_f(self):
+        key = self._weight_key()
+        if key != self.wf_version:
+            ops.pack_weights_fprop(self.conv.weight.detach(), self.taps, self.cout_pad, self.cin_pad, out=self.wf)
+            self.wf_version = key
+
+    def _pack_d(self):
+        key = self._weight_key()
+        if key != self.wd_version:
+            ops.pack_weights_dgrad(self.conv.weight.detach(), self.cout_pad, self.cin_pad, out=self.wd)
+            self.wd_version = key
+
+    def forward_train(self, pool_out=None, code=None):
+        p, bn = self.plan, self.bn
+        self._pack_f()
+        parts = p.parts_view(self.cout_pad)
+        ops.conv3x3(self.x, self.wf, self.y, taps=self.taps, stat_partials=parts)
+        v = self.vec
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        track = bn.track_running_stats and bn.running_mean is not None
+        ops.bn_finalize(parts, p.stat_rows, self.cout, self.cout_pad, self.count, bn.weight.detach(),
+                        bn.bias.detach(), self.conv.bias.detach() if self.conv.bias is not None else None,
+                        bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
+                        v[0], v[1], v[2], v[3])
+        if pool_out is not None:
+            ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
+        else:
+            ops.bn_relu_apply(self.y, v[2], v[3], self.a)
+
+    def forward_eval(self):
+        """BatchNorm folded into the conv epilogue with the running statistics (models/unet.py:12 in eval mode)."""
+        bn = self.bn
+        self._pack_f()
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               self.conv.bias._version if self.conv.bias is not None else 0, bn.weight.data_ptr())
+        if getattr(self, "_fold_key", None) != key:
+            with torch.no_grad():
+                scale = torch.zeros(self.cout_pad, device=self.x.device)
+                shift = torch.zeros(self.cout_pad, device=self.x.device)
+                s = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+                b = self.conv.bias.detach() if self.conv.bias is not None else 0.0
+                scale[:self.cout] = s
+                shift[:self.cout] = bn.bias.detach() + (b - bn.running_mean) * s
+            self._fold = (scale, shift)
+            self._fold_key = key
+        ops.conv3x3(self.x, self.wf, self.a, taps=self.taps, scale=self._fold[0], shift=self._fold[1], relu=True)
+
+    def backward(self, da, dx, flat):
+        """da: gradient w.r.t. self.a (same view geometry); dx: view receiving the gradient w.r.t. self.x or None."""
+        p, v = self.plan, self.vec
+        parts = p.parts_view(self.cout_pad)
+        ops.bn_relu_bwd_reduce(da, self.y, v[2], v[3], parts, p.reduce_rows)
+        dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
+        dbeta = flat[self.g_beta:self.g_beta + self.cout]
+        ops.bn_bwd_finalize(parts, p.reduce_rows, self.cout, self.cout_pad, self.count, self.bn.weight.detach(), v[0],
+                            v[1], dgamma, dbeta, self.coef)
+        ops.bn_relu_bwd_apply(da, self.y, v[2], v[3], self.coef, self.y)  # y now holds dy
+        dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
+        ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace)
+        if self.g_b is not None:
+            flat[self.g_b:self.g_b + self.cout].zero_()  # conv bias feeds a batch-stat BatchNorm: gradient is exactly 0
+        if dx is not None:
+            self._pack_d()
+            ops.conv3x3(self.y, self.wd, dx)
+
+
+class Plan:
+    """Buffers + kernel sequences for one input geometry. Subclasses define the topology."""
+
+    def __init__(self, module, n, h, w, device):
+        self.module, self.n, self.h, self.w, self.device = module, n, h, w, device
+        self.stat_rows = ops.stat_rows()
+        self.reduce_rows = 4 * ops.sm_count()
+        self.parts = torch.empty(max(self.stat_rows, self.reduce_rows), 2, 1024, device=device)
+        self.blocks = []  # in forward order
+        self.workspace = None
+        self.generation = 0
+        self.grad_ready = None  # optional callback(lo, hi) on flat gradient ranges, in completion order
+
+    def parts_view(self, c):
+        rows = self.parts.shape[0]
+        return self.parts.view(-1)[:rows * 2 * c].view(rows, 2, c)
+
+    def buf(self, h, w, c, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(self.n, h, w, c, dtype=torch.bfloat16, device=self.device)
+
+    def add(self, name, seq, x, a, taps=9):
+        conv, bn = seq[0], seq[1]
+        b = Block(self, name, conv, bn, x, a, taps)
+        self.blocks.append(b)
+        return b
+
+    def finish(self):
+        self.workspace = torch.empty(max(b.ws_bytes for b in self.blocks), dtype=torch.uint8, device=self.device)
+        # flat gradient layout in backward completion order (last block first): contiguous ready ranges for the
+        # data-parallel all-reduce buckets
+        off = 0
+        for b in reversed(self.blocks):
+            b.g_w = off
+            off += b.conv.weight.numel()
+            if b.conv.bias is not None:
+                b.g_b = off
+                off += b.cout
+            b.g_gamma = off
+            off += b.cout
+            b.g_beta = off
+            off += b.cout
+            b.g_end = off
+        self.flat_size = off
+
+    def param_list(self):
+        out = []
+        for b in self.blocks:
+            out += [q for q in b.params() if q is not None]
+        return out
+
+    def grads_for(self, flat):
+        out = []
+        for b in self.blocks:
+            out.append(flat[b.g_w:b.g_w + b.conv.weight.numel()].view_as(b.conv.weight))
+            if b.conv.bias is not None:
+                out.append(flat[b.g_b:b.g_b + b.cout])
+            out.append(flat[b.g_gamma:b.g_gamma + b.cout])
+            out.append(flat[b.g_beta:b.g_beta + b.cout])
+        return out
+
+    def _bump_batches_tracked(self):
+        t = [b.bn.num_batches_tracked for b in self.blocks if b.bn.num_batches_tracked is not None]
+        if t:
+            torch._foreach_add_(t, 1)
+
+    def _done(self, b):
+        if self.grad_ready is not None:
+            self.grad_ready(b.g_w, b.g_end)
+
+
+class UNetPlan(Plan):
+    """models/unet.py:94-156. Skip concatenation is by construction: the encoder block and the up-conv block write
+    their activations straight into channel slices of the shared concat buffer ([up | skip], upsampled branch first,
+    models/unet.py:124); F.pad (models/unet.py:120-123) is the zero border of that buffer."""
+
+    def __init__(self, m, n, h, w, device):
+        super().__init__(m, n, h, w, device)
+        self.class_num = m.class_num
+        hs = [h]
+        ws = [w]
+        for _ in range(4):
+            hs.append(hs[-1] // 2)
+            ws.append(ws[-1] // 2)
+        ch = [64, 128, 256, 512, 1024]
+        self.cols = self.buf(h, w, 64)
+        # concat buffers at levels 0..3: channels [0, ch[l]) = upsampled branch, [ch[l], 2 ch[l]) = encoder skip
+        self.cat = [self.buf(hs[l], ws[l], 2 * ch[l], zero=True) for l in range(4)]
+        self.dcat = [self.buf(hs[l], ws[l], 2 * ch[l]) for l in range(4)]
+        downs = [m.down1, m.down2, m.down3, m.down4, m.down5]
+        self.enc = []
+        x = self.cols
+        self.pooled, self.dpooled, self.enc_mid, self.d_enc_mid = [], [], [], []
+        for l in range(5):
+            mid = self.buf(hs[l], ws[l], ch[l])
+            self.enc_mid.append(mid)
+            self.d_enc_mid.append(torch.empty_like(mid))
+            b0 = self.add(f"down{l + 1}.0", downs[l][0].conv, x, mid, taps=1 if l == 0 else 9)
+            if l < 4:
+                out = self.cat[l][..., ch[l]:]
+                pooled = self.buf(hs[l + 1], ws[l + 1], ch[l])
+                self.pooled.append(pooled)
+                self.dpooled.append(torch.empty_like(pooled))
+            else:
+                out = self.buf(hs[l], ws[l], ch[l])
+                self.bott, self.dbott = out, torch.empty_like(out)
+            b1 = self.add(f"down{l + 1}.1", downs[l][1].conv, mid, out)
+            self.enc.append((b0, b1))
+            if l < 4:
+                x = pooled
+        ups = [(m.upsample1, m.up1), (m.upsample2, m.up2), (m.upsample3, m.up3), (m.upsample4, m.up4)]
+        self.dec = []
+        x = self.bott
+        dx = self.dbott
+        for i, (upm, seq) in enumerate(ups):
+            l = 3 - i  # level of the concat buffer this stage writes into
+            hu, wu = 2 * x.shape[1], 2 * x.shape[2]
+            c_in = x.shape[3]
+            up = self.buf(hu, wu, c_in)
+            dup = torch.empty_like(up)
+            dh, dw = hs[l] - hu, ws[l] - wu
+            top, left = dh // 2, dw // 2  # F.pad offsets, models/unet.py:122-123
+            win = (slice(None), slice(top, top + hu), slice(left, left + wu), slice(0, ch[l]))
+            bu = self.add(f"upsample{i + 1}", upm.conv.conv, up, self.cat[l][win])
+            m0 = self.buf(hs[l], ws[l], ch[l])
+            m1 = self.buf(hs[l], ws[l], ch[l])
+            b0 = self.add(f"up{i + 1}.0", seq[0].conv, self.cat[l], m0)
+            b1 = self.add(f"up{i + 1}.1", seq[1].conv, m0, m1)
+            self.dec.append(dict(src=x, dsrc=dx, up=up, dup=dup, win=win, bu=bu, b0=b0, b1=b1, m0=m0, m1=m1,
+                                 dm0=torch.empty_like(m0), dm1=torch.empty_like(m1), level=l))
+            x, dx = m1, self.dec[-1]["dm1"]
+        self.out_a = self.buf(h, w, pad64(self.class_num))
+        self.d_out_a = torch.empty_like(self.out_a)
+        self.b_out = self.add("output", m.output.conv, x, self.out_a)
+        self.finish()
+
+    def forward(self, x, train):
+        ops.im2col3x3(x, self.cols)
+        for l, (b0, b1) in enumerate(self.enc):
+            if train:
+                b0.forward_train()
+                if l < 4:
+                    b1.forward_train(pool_out=self.pooled[l])
+                else:
+                    b1.forward_train()
+            else:
+                b0.forward_eval()
+                b1.forward_eval()
+                if l < 4:
+                    ops.maxpool2x2(b1.a, self.pooled[l])
+        for d in self.dec:
+            ops.bilinear2x(d["src"], d["up"])
+            for b in (d["bu"], d["b0"], d["b1"]):
+                b.forward_train() if train else b.forward_eval()
+        self.b_out.forward_train() if train else self.b_out.forward_eval()
+        if train:
+            self._bump_batches_tracked()
+        logits = torch.empty(self.n, self.class_num, self.h, self.w, device=self.device)
+        ops.nhwc_to_nchw(self.out_a, logits)
+        return logits
+
+    def backward(self, dlogits):
+        flat = torch.empty(self.flat_size, device=self.device)
+        ops.nchw_to_nhwc(dlogits, self.d_out_a)
+        last = self.dec[-1]
+        self.b_out.backward(self.d_out_a, last["dm1"], flat)
+        self._done(self.b_out)
+        for d in reversed(self.dec):
+            l = d["level"]
+            d["b1"].backward(d["dm1"], d["dm0"], flat)
+            self._done(d["b1"])
+            d["b0"].backward(d["dm0"], self.dcat[l], flat)
+            self._done(d["b0"])
+            d["bu"].backward(self.dcat[l][d["win"]], d["dup"], flat)
+            self._done(d["bu"])
+            ops.bilinear2x_bwd(d["dup"], d["dsrc"])
+        for l in range(4, -1, -1):
+            b0, b1 = self.enc[l]
+            if l == 4:
+                da = self.dbott
+            else:
+                ch = self.cat[l].shape[3] // 2
+                da = self.dcat[l][..., ch:]
+                # encoder activation feeds both the skip (already in dcat) and the pool: add the pool path
+                ops.maxpool2x2_bwd(self.dpooled[l], da, x=b1.a, accumulate=True)
+            b1.backward(da, self.d_enc_mid[l], flat)
+            self._done(b1)
+            b0.backward(self.d_enc_mid[l], self.dpooled[l - 1] if l > 0 else None, flat)
+            self._done(b0)
+        return flat
+
+
+class SegNetPlan(Plan):
+    """models/segnet.py:82-119. MaxPool indices are 1-byte window codes local to the plan (the reference never
+    exposes idx1..idx5 either); MaxUnpool writes into a plane of the saved encoder shape (output_size=fmK)."""
+
+    ENC = [2, 2, 3, 3, 3]
+
+    def __init__(self, m, n, h, w, device):
+        super().__init__(m, n, h, w, device)
+        self.class_num = m.class_num
+        encs = [m.encoder1, m.encoder2, m.encoder3, m.encoder4, m.encoder5]
+        decs = [m.decoder5, m.decoder4, m.decoder3, m.decoder2, m.decoder1]
+        self.cols = self.buf(h, w, 64)
+        self.stages = []  # encoder stages: blocks, activations, pooled, code
+        x = self.cols
+        ch_, cw_ = h, w
+        for s, seq in enumerate(encs):
+            blocks, acts, dacts = [], [], []
+            for j, bc in enumerate(seq):
+                a = self.buf(ch_, cw_, pad64(bc.conv.out_channels))
+                blocks.append(self.add(f"encoder{s + 1}.{j}", (bc.conv, bc.bn), x, a, taps=1 if (s == 0 and j == 0) else 9))
+                acts.append(a)
+                dacts.append(torch.empty_like(a))
+                x = a
+            pooled = self.buf(ch_ // 2, cw_ // 2, x.shape[3])
+            code = torch.empty(n, ch_ // 2, cw_ // 2, x.shape[3], dtype=torch.uint8, device=device)
+            self.stages.append(dict(blocks=blocks, acts=acts, dacts=dacts, pooled=pooled, dpooled=torch.empty_like(pooled),
+                                    code=code, shape=(ch_, cw_)))
+            x = pooled
+            ch_, cw_ = ch_ // 2, cw_ // 2
+        self.dstages = []
+        dx = self.stages[-1]["dpooled"]
+        for i, seq in enumerate(decs):
+            st = self.stages[4 - i]
+            hh, ww = st["shape"]
+            un = self.buf(hh, ww, x.shape[3])
+            dun = torch.empty_like(un)
+            blocks, acts, dacts = [], [], []
+            xin = un
+            for j, bc in enumerate(seq):
+                a = self.buf(hh, ww, pad64(bc.conv.out_channels))
+                blocks.append(self.add(f"decoder{5 - i}.{j}", (bc.conv, bc.bn), xin, a))
+                acts.append(a)
+                dacts.append(torch.empty_like(a))
+                xin = a
+            self.dstages.append(dict(src=x, dsrc=dx, un=un, dun=dun, code=st["code"], blocks=blocks, acts=acts,
+                                     dacts=dacts))
+            x, dx = xin, dacts[-1]
+        self.out_a, self.d_out_a = x, dx
+        self.finish()
+
+    def forward(self, x, train):
+        ops.im2col3x3(x, self.cols)
+        for st in self.stages:
+            bl = st["blocks"]
+            for j, b in enumerate(bl):
+                if train:
+                    if j == len(bl) - 1:
+                        b.forward_train(pool_out=st["pooled"], code=st["code"])
+                    else:
+                        b.forward_train()
+                else:
+                    b.forward_eval()
+            if not train:
+                ops.maxpool2x2(bl[-1].a, st["pooled"], st["code"])
+        for ds in self.dstages:
+            ops.maxunpool2x2(ds["src"], ds["code"], ds["un"])
+            for b in ds["blocks"]:
+                b.forward_train() if train else b.forward_eval()
+        if train:
+            self._bump_batches_tracked()
+        logits = torch.empty(self.n, self.class_num, self.h, self.w, device=self.device)
+        ops.nhwc_to_nchw(self.out_a, logits)
+        return logits
+
+    def backward(self, dlogits):
+        flat = torch.empty(self.flat_size, device=self.device)
+        ops.nchw_to_nhwc(dlogits, self.d_out_a)
+        for ds in reversed(self.dstages):
+            bl = ds["blocks"]
+            for j in range(len(bl) - 1, -1, -1):
+                bl[j].backward(ds["dacts"][j], ds["dacts"][j - 1] if j > 0 else ds["dun"], flat)
+                self._done(bl[j])
+            ops.maxunpool2x2_bwd(ds["dun"], ds["code"], ds["dsrc"])
+        for s in range(4, -1, -1):
+            st = self.stages[s]
+            bl = st["blocks"]
+            ops.maxpool2x2_bwd(st["dpooled"], st["dacts"][-1], code=st["code"])
+            for j in range(len(bl) - 1, -1, -1):
+                if j > 0:
+                    dx = st["dacts"][j - 1]
+                else:
+                    dx = self.stages[s - 1]["dpooled"] if s > 0 else None
+                bl[j].backward(st["dacts"][j], dx, flat)
+                self._done(bl[j])
+        return flat
+
+
+class _NetFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward/backward are the plan's kernel sequences."""
+
+    @staticmethod
+    def forward(ctx, x, plan, *params):
+        ctx.plan = plan
+        plan.generation += 1
+        ctx.generation = plan.generation
+        return plan.forward(x, True)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan = ctx.plan
+        if ctx.generation != plan.generation:
+            raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
+                               "later forward of the same module and input shape (plans own one set of buffers)")
+        flat = plan.backward(dlogits.float().contiguous())
+        return (None, None) + tuple(plan.grads_for(flat))
+
+
+def run_module(module, plan_cls, x):
+    """Shared forward of the drop-in modules: x fp32 NCHW CUDA -> logits fp32 NCHW."""
+    if not x.is_cuda:
+        raise RuntimeError("camvid_b200 runs on CUDA (sm_100a) only: move the module and its input to the GPU; "
+                           "there is no CPU path")
+    if x.dim() != 4 or x.shape[1] != module.input_channels:
+        raise RuntimeError(f"expected input [N,{module.input_channels},H,W], got {tuple(x.shape)}")
+    if x.shape[1] * 9 > 64:
+        raise RuntimeError("input_channels > 7 is not supported by the first-layer im2col kernel")
+    if x.shape[2] < 32 or x.shape[3] < 32:
+        raise RuntimeError("input must be at least 32x32 (five 2x2 poolings)")
+    x = x.detach().float().contiguous()
+    n, _, h, w = x.shape
+    key = (n, h, w, x.device.index)
+    plans = module.__dict__.setdefault("_plans", {})
+    plan = plans.get(key)
+    if plan is None or any(b.conv.weight.device != x.device for b in plan.blocks[:1]):
+        plan = plan_cls(module, n, h, w, x.device)
+        plans[key] = plan
+    if module.training:
+        if torch.is_grad_enabled():
+            return _NetFunction.apply(x, plan, *plan.param_list())
+        return plan.forward(x, True)
+    return plan.forward(x, False)

@@ -233,9 +233,18 @@ def softmax_ce_nhwc(logits, c, target, ignore_index, loss_sum_count, dlogits, gr
                "softmax_ce_nhwc_bf16")
 
 
-def confusion_matrix(pred, gt, c, cm):
-    _lib.check(_lib.load().cvb_confusion_matrix(_ptr(pred), _ptr(gt), pred.numel(), c, _ptr(cm), _stream()),
-               "confusion_matrix")
+NO_IGNORE = -(2 ** 62)
+
+
+def confusion_matrix(pred, gt, c, cm, ignore_label=NO_IGNORE, clamp_oob=False):
+    """cm[gt, pred] += counts over int64 label tensors (any shape, same numel)."""
+    for t, nm in ((pred, "pred"), (gt, "gt")):
+        if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+            raise RuntimeError(f"confusion_matrix.{nm}: expected a contiguous CUDA int64 tensor")
+    if pred.numel() != gt.numel():
+        raise RuntimeError("confusion_matrix: pred and gt sizes differ")
+    _lib.check(_lib.load().cvb_confusion_matrix(_ptr(pred), _ptr(gt), pred.numel(), c, ignore_label,
+                                                1 if clamp_oob else 0, _ptr(cm), _stream()), "confusion_matrix")
     return cm
 
 
