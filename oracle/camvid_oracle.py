@@ -23,13 +23,115 @@ import torch.nn.functional as F
 # ----------------------------------------------------------------------------------------------------------------
 # building block: conv3x3(pad 1, bias) -> BatchNorm2d -> ReLU   (models/unet.py:5-17, models/segnet.py:5-17)
 # ----------------------------------------------------------------------------------------------------------------
+RECORD = None  # tests may set this to a dict; filled with block name -> {"x", "out"} and, by train_step, {"dx", "dout"}
+STORAGE = "fp32"  # "fp32": the reference's arithmetic. "bf16": the same network with the north_star's storage format
+
+
 def _cbr(x, sd, conv, bn, train, momentum=0.1, eps=1e-5):
+    impl = _cbr_impl if STORAGE == "fp32" else _cbr_bf16
+    out = impl(x, sd, conv, bn, train, momentum, eps)
+    if RECORD is not None:
+        RECORD[conv.rsplit(".conv", 1)[0] if conv.endswith(".conv") else conv[:-len(".conv.0")]] = {"x": x, "out": out}
+    return out
+
+
+def _cbr_impl(x, sd, conv, bn, train, momentum=0.1, eps=1e-5):
     y = F.conv2d(x, sd[conv + ".weight"], sd[conv + ".bias"], padding=1)
     y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"],
                      train, momentum, eps)
     if train and (bn + ".num_batches_tracked") in sd:
         sd[bn + ".num_batches_tracked"] += 1
     return F.relu(y)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bf16 storage model (STORAGE = "bf16").  BASELINE.json's north_star fixes the format of the accelerated path:
+# "NHWC bf16 with fp32 accumulate".  This is the reference network with exactly that and nothing else changed:
+# conv operands (activations, weights), conv outputs, activations and activation gradients are HELD in bf16 (rounded
+# to nearest-even at the point they would be stored); every sum, statistic, normalisation, interpolation and the loss
+# is fp32, like the reference.  It exists because the network is chaotic at random init (a perturbation grows about
+# x1.2 per conv+BN+ReLU block, tools/precision_sim.py), so ANY bf16 implementation -- including the reference under
+# torch autocast -- sits ~1e-1 away from the fp32 logits; the CUDA path is checked tightly against this model and,
+# block by block on identical inputs, against the fp32 reference.
+# ----------------------------------------------------------------------------------------------------------------
+def _r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _StoreBF16(torch.autograd.Function):
+    """y = bf16(x) in forward and/or g = bf16(g) in backward (a tensor and its gradient written to a bf16 buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return _r(x) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (_r(g) if ctx.bwd else g), None, None
+
+
+class _BlockBF16(torch.autograd.Function):
+    """conv3x3 -> BatchNorm(batch statistics) -> ReLU with bf16 storage; backward restated with the same storage
+    points (dy and dx held in bf16, reductions and parameter gradients fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, eps):
+        x16, w16 = _r(x), _r(w)
+        y32 = F.conv2d(x16, w16, None, padding=1)  # the bias cancels under batch statistics
+        n = y32.numel() // y32.shape[1]
+        mean = y32.double().mean((0, 2, 3))
+        var = (y32.double() ** 2).mean((0, 2, 3)) - mean ** 2
+        invstd = (1.0 / torch.sqrt(var.clamp_min(0) + eps)).float()
+        mean = mean.float()
+        scale = gamma * invstd
+        shift = beta - mean * scale
+        y16 = _r(y32)
+        z = y16 * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        ctx.save_for_backward(x16, w16, y16, z > 0, mean, invstd, gamma)
+        ctx.n = n
+        ctx.mark_non_differentiable(mean, var)
+        return _r(F.relu(z)), mean, var.float()
+
+    @staticmethod
+    def backward(ctx, da, _m, _v):
+        x16, w16, y16, pos, mean, invstd, gamma = ctx.saved_tensors
+        n = ctx.n
+        g = da * pos
+        sg = g.double().sum((0, 2, 3))
+        sgy = (g.double() * y16.double()).sum((0, 2, 3))
+        dgamma = invstd.double() * (sgy - mean.double() * sg)
+        dbeta = sg
+        sc = (gamma * invstd).double()
+        c0 = sc.float().view(1, -1, 1, 1)
+        c1 = (-sc * invstd.double() * dgamma / n).float().view(1, -1, 1, 1)
+        c2 = (-sc * dbeta / n + sc * mean.double() * invstd.double() * dgamma / n).float().view(1, -1, 1, 1)
+        dy16 = _r(g * c0 + (y16 * c1 + c2))
+        dw = torch.nn.grad.conv2d_weight(x16, w16.shape, dy16, padding=1)
+        dx = _r(torch.nn.grad.conv2d_input(x16.shape, w16, dy16, padding=1)) if ctx.needs_input_grad[0] else None
+        return dx, dw, dgamma.float(), dbeta.float(), None
+
+
+def _cbr_bf16(x, sd, conv, bn, train, momentum=0.1, eps=1e-5):
+    w, b = sd[conv + ".weight"], sd[conv + ".bias"]
+    gamma, beta = sd[bn + ".weight"], sd[bn + ".bias"]
+    if not train:  # BatchNorm folded into the conv epilogue: one rounding, of the activation
+        s = gamma * torch.rsqrt(sd[bn + ".running_var"] + eps)
+        acc = F.conv2d(_r(x), _r(w), None, padding=1)
+        return _r(F.relu(acc * s.view(1, -1, 1, 1) + (beta + (b - sd[bn + ".running_mean"]) * s).view(1, -1, 1, 1)))
+    a, mean, var = _BlockBF16.apply(x, w, gamma, beta, eps)
+    with torch.no_grad():
+        n = a.numel() // a.shape[1]
+        sd[bn + ".running_mean"].mul_(1 - momentum).add_(momentum * (mean + b.detach()))
+        sd[bn + ".running_var"].mul_(1 - momentum).add_(momentum * var * (n / max(n - 1, 1)))
+        if (bn + ".num_batches_tracked") in sd:
+            sd[bn + ".num_batches_tracked"] += 1
+    return _StoreBF16.apply(a, False, True)  # gradients from several consumers are summed, then stored in bf16
+
+
+def _held(x, fwd=True, bwd=True):
+    """Marks a tensor (and its gradient) as written to a bf16 buffer; identity under fp32 storage."""
+    return x if STORAGE == "fp32" else _StoreBF16.apply(x, fwd, bwd)
 
 
 def _unet_block(x, sd, prefix, train):
@@ -40,6 +142,7 @@ def _unet_block(x, sd, prefix, train):
 def unet_forward(sd, x, train=True):
     """models/unet.py:94-156. `sd`: dict name -> tensor (running stats are updated in place when train)."""
     skips = []
+    x = _held(x, True, False)
     for level in range(1, 6):
         x = _unet_block(x, sd, f"down{level}.0", train)
         x = _unet_block(x, sd, f"down{level}.1", train)
@@ -48,14 +151,14 @@ def unet_forward(sd, x, train=True):
             x = F.max_pool2d(x, 2, 2)  # models/unet.py:92,100-109
     for stage in range(1, 5):
         skip = skips[4 - stage]
-        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)  # models/unet.py:25,29
+        x = _held(F.interpolate(_held(x, False, True), scale_factor=2, mode="bilinear", align_corners=True))  # :25,29
         x = _unet_block(x, sd, f"upsample{stage}.conv", train)
         dh, dw = skip.size(2) - x.size(2), skip.size(3) - x.size(3)
         x = F.pad(x, [dw // 2, dw - dw // 2, dh // 2, dh - dh // 2])  # models/unet.py:120-123
         x = torch.cat([x, skip], dim=1)  # upsampled branch first, models/unet.py:124
         x = _unet_block(x, sd, f"up{stage}.0", train)
         x = _unet_block(x, sd, f"up{stage}.1", train)
-    return _unet_block(x, sd, "output", train)  # models/unet.py:91,154 (logits are post-ReLU)
+    return _held(_unet_block(x, sd, "output", train), False, True)  # models/unet.py:91,154 (logits are post-ReLU)
 
 
 SEGNET_DEPTH = (2, 2, 3, 3, 3)
@@ -64,6 +167,7 @@ SEGNET_DEPTH = (2, 2, 3, 3, 3)
 def segnet_forward(sd, x, train=True, return_indices=False):
     """models/segnet.py:82-119."""
     shapes, indices = [], []
+    x = _held(x, True, False)
     for s in range(1, 6):
         for j in range(SEGNET_DEPTH[s - 1]):
             x = _cbr(x, sd, f"encoder{s}.{j}.conv", f"encoder{s}.{j}.bn", train)
@@ -74,6 +178,7 @@ def segnet_forward(sd, x, train=True, return_indices=False):
         x = F.max_unpool2d(x, indices[s - 1], 2, output_size=shapes[s - 1])  # models/segnet.py:80,104-116
         for j in range(SEGNET_DEPTH[s - 1]):
             x = _cbr(x, sd, f"decoder{s}.{j}.conv", f"decoder{s}.{j}.bn", train)
+    x = _held(x, False, True)
     return (x, indices) if return_indices else x
 
 
@@ -85,8 +190,28 @@ def cross_entropy(logits, target, ignore_index=-100):
     return F.cross_entropy(logits, target, ignore_index=ignore_index)
 
 
-def train_step(name, sd, x, target, ignore_index=-100):
-    """One forward + backward of train.py:128-131 on a copy of `sd`. Returns (loss, logits, grads, new_sd)."""
+def train_step(name, sd, x, target, ignore_index=-100, storage="fp32"):
+    """One forward + backward of train.py:128-131 on a copy of `sd`. Returns (loss, logits, grads, new_sd).
+    storage="bf16" runs the bf16 storage model of the same network (see above)."""
+    global STORAGE
+    prev, STORAGE = STORAGE, storage
+    try:
+        return _train_step(name, sd, x, target, ignore_index)
+    finally:
+        STORAGE = prev
+
+
+def forward(name, sd, x, train=False, storage="fp32"):
+    global STORAGE
+    prev, STORAGE = STORAGE, storage
+    try:
+        with torch.no_grad():
+            return FORWARD[name](sd, x, train)
+    finally:
+        STORAGE = prev
+
+
+def _train_step(name, sd, x, target, ignore_index):
     sd = {k: v.clone() for k, v in sd.items()}
     leaves = {}
     for k, v in sd.items():
@@ -94,7 +219,19 @@ def train_step(name, sd, x, target, ignore_index=-100):
             leaves[k] = sd[k] = v.detach().requires_grad_(True)
     logits = FORWARD[name](sd, x, True)
     loss = cross_entropy(logits, target, ignore_index)
-    grads = torch.autograd.grad(loss, list(leaves.values()))
+    extra = []
+    if RECORD is not None:  # also differentiate w.r.t. every block's input and output (teacher-forced block tests)
+        for rec in RECORD.values():
+            extra += [rec["out"]] + ([rec["x"]] if rec["x"].requires_grad else [])
+    grads = torch.autograd.grad(loss, list(leaves.values()) + extra, allow_unused=True)
+    if RECORD is not None:
+        it = iter(grads[len(leaves):])
+        for rec in RECORD.values():
+            rec["dout"] = next(it)
+            rec["dx"] = next(it) if rec["x"].requires_grad else None
+            rec["x"], rec["out"] = rec["x"].detach(), rec["out"].detach()
+    grads = grads[:len(leaves)]
+    grads = [torch.zeros_like(p) if g is None else g for p, g in zip(leaves.values(), grads)]  # bf16 model: conv bias
     return loss.detach(), logits.detach(), dict(zip(leaves.keys(), grads)), {k: v.detach() for k, v in sd.items()}
 
 

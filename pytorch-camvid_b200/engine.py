@@ -34,6 +34,8 @@ class Block:
         self.wd = None if taps == 1 else torch.empty(self.cin_pad, 9 * self.cout_pad, dtype=torch.bfloat16, device=dev)
         self.wf_version = self.wd_version = None
         self.ws_bytes = ops.conv3x3_wgrad_workspace_bytes(x, self.y, taps)
+        self.flops = 2.0 * 9 * self.cin * self.cout * self.count  # algorithmic FLOPs of one pass (un-padded channels)
+        self.c_ratio = self.cout / self.cout_pad
         # offsets into the flat gradient buffer, assigned by the plan
         self.g_w = self.g_b = self.g_gamma = self.g_beta = None
 
@@ -61,7 +63,8 @@ class Block:
         p, bn = self.plan, self.bn
         self._pack_f()
         parts = p.parts_view(self.cout_pad)
-        ops.conv3x3(self.x, self.wf, self.y, taps=self.taps, stat_partials=parts)
+        ops.conv3x3(self.x, self.wf, self.y, taps=self.taps, stat_partials=parts, algo_flops=self.flops)
+        ops.WORK_SCALE = self.c_ratio
         v = self.vec
         momentum = 0.1 if bn.momentum is None else bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
@@ -73,6 +76,7 @@ class Block:
             ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
         else:
             ops.bn_relu_apply(self.y, v[2], v[3], self.a)
+        ops.WORK_SCALE = 1.0
 
     def forward_eval(self):
         """BatchNorm folded into the conv epilogue with the running statistics (models/unet.py:12 in eval mode)."""
@@ -90,25 +94,28 @@ class Block:
                 shift[:self.cout] = bn.bias.detach() + (b - bn.running_mean) * s
             self._fold = (scale, shift)
             self._fold_key = key
-        ops.conv3x3(self.x, self.wf, self.a, taps=self.taps, scale=self._fold[0], shift=self._fold[1], relu=True)
+        ops.conv3x3(self.x, self.wf, self.a, taps=self.taps, scale=self._fold[0], shift=self._fold[1], relu=True,
+                    algo_flops=self.flops)
 
     def backward(self, da, dx, flat):
         """da: gradient w.r.t. self.a (same view geometry); dx: view receiving the gradient w.r.t. self.x or None."""
         p, v = self.plan, self.vec
         parts = p.parts_view(self.cout_pad)
+        ops.WORK_SCALE = self.c_ratio
         ops.bn_relu_bwd_reduce(da, self.y, v[2], v[3], parts, p.reduce_rows)
         dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
         dbeta = flat[self.g_beta:self.g_beta + self.cout]
         ops.bn_bwd_finalize(parts, p.reduce_rows, self.cout, self.cout_pad, self.count, self.bn.weight.detach(), v[0],
                             v[1], dgamma, dbeta, self.coef)
         ops.bn_relu_bwd_apply(da, self.y, v[2], v[3], self.coef, self.y)  # y now holds dy
+        ops.WORK_SCALE = 1.0
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
-        ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace)
+        ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         if self.g_b is not None:
             flat[self.g_b:self.g_b + self.cout].zero_()  # conv bias feeds a batch-stat BatchNorm: gradient is exactly 0
         if dx is not None:
             self._pack_d()
-            ops.conv3x3(self.y, self.wd, dx)
+            ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops)
 
 
 class Plan:
@@ -122,7 +129,7 @@ class Plan:
         self.blocks = []  # in forward order
         self.workspace = None
         self.generation = 0
-        self.grad_ready = None  # optional callback(lo, hi) on flat gradient ranges, in completion order
+        self.reducer = None  # parallel.GradReducer of the module during a backward pass (data parallelism)
 
     def parts_view(self, c):
         rows = self.parts.shape[0]
@@ -177,9 +184,23 @@ class Plan:
         if t:
             torch._foreach_add_(t, 1)
 
+    def _begin_backward(self):
+        """Flat fp32 gradient buffer of this pass; under data parallelism its ranges are all-reduced as they fill."""
+        flat = torch.empty(self.flat_size, device=self.device)
+        self.reducer = self.module.__dict__.get("_cvb_reducer")
+        if self.reducer is not None:
+            self.reducer.begin(flat)
+        return flat
+
     def _done(self, b):
-        if self.grad_ready is not None:
-            self.grad_ready(b.g_w, b.g_end)
+        if self.reducer is not None:
+            self.reducer.ready(b.g_w, b.g_end)
+
+    def _end_backward(self, flat):
+        if self.reducer is not None:
+            self.reducer.finish()
+            self.reducer = None
+        return flat
 
 
 class UNetPlan(Plan):
@@ -273,7 +294,7 @@ class UNetPlan(Plan):
         return logits
 
     def backward(self, dlogits):
-        flat = torch.empty(self.flat_size, device=self.device)
+        flat = self._begin_backward()
         ops.nchw_to_nhwc(dlogits, self.d_out_a)
         last = self.dec[-1]
         self.b_out.backward(self.d_out_a, last["dm1"], flat)
@@ -300,7 +321,7 @@ class UNetPlan(Plan):
             self._done(b1)
             b0.backward(self.d_enc_mid[l], self.dpooled[l - 1] if l > 0 else None, flat)
             self._done(b0)
-        return flat
+        return self._end_backward(flat)
 
 
 class SegNetPlan(Plan):
@@ -378,7 +399,7 @@ class SegNetPlan(Plan):
         return logits
 
     def backward(self, dlogits):
-        flat = torch.empty(self.flat_size, device=self.device)
+        flat = self._begin_backward()
         ops.nchw_to_nhwc(dlogits, self.d_out_a)
         for ds in reversed(self.dstages):
             bl = ds["blocks"]
@@ -397,7 +418,7 @@ class SegNetPlan(Plan):
                     dx = self.stages[s - 1]["dpooled"] if s > 0 else None
                 bl[j].backward(st["dacts"][j], dx, flat)
                 self._done(bl[j])
-        return flat
+        return self._end_backward(flat)
 
 
 class _NetFunction(torch.autograd.Function):

@@ -12,6 +12,46 @@ from . import _lib
 from ._lib import ConvEpilogue, View
 
 
+LAUNCHES = 0  # kernels enqueued through the C ABI by this process (bench.py reports the per-step count)
+_PROFILE = None  # while kernel timing is on: list of (entry point, algorithmic work, start event, end event)
+WORK_SCALE = 1.0  # real / padded channel ratio of the block being run (engine sets it; algorithmic-byte accounting)
+
+
+def profile(on=True):
+    """Turns per-call CUDA-event timing on (returns the record list) or off. Measurement aid of bench.py: events are
+    recorded on torch's current stream, which is the stream every kernel is enqueued on."""
+    global _PROFILE
+    _PROFILE = [] if on else None
+    return _PROFILE
+
+
+def _call(what, kernels, work, fn, *args):
+    """One C-ABI call: counts its kernel launches, optionally brackets it with CUDA events, raises on failure.
+    work = ("bytes" | "flops", algorithmic amount) for the roofline arithmetic."""
+    global LAUNCHES
+    LAUNCHES += kernels
+    prof = _PROFILE
+    if prof is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        prof.append((what, work, e0, e1))
+    if rc != 0:
+        _lib.check(rc, what)
+
+
+def _nbytes(*ts):
+    """Algorithmic bytes of dense passes over these tensors (bf16 views count their real channels)."""
+    tot = 0.0
+    for t in ts:
+        if t is not None:
+            tot += t.numel() * t.element_size() * (WORK_SCALE if t.dtype == torch.bfloat16 else 1.0)
+    return ("bytes", tot)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -55,25 +95,28 @@ def stat_rows():
 def nchw_to_nhwc(src, dst):
     """src fp32 [N,C,H,W] contiguous -> dst NHWC bf16 view (extra channels zeroed)."""
     _f32(src, "nchw_to_nhwc.src")
-    _lib.check(_lib.load().cvb_nchw_f32_to_nhwc_bf16(_ptr(src), src.shape[1], view(dst), _stream()), "nchw_to_nhwc")
+    _call("nchw_to_nhwc", 1, _nbytes(src, dst), _lib.load().cvb_nchw_f32_to_nhwc_bf16, _ptr(src), src.shape[1],
+          view(dst), _stream())
     return dst
 
 
 def nhwc_to_nchw(src, dst):
     """src NHWC bf16 view -> dst fp32 [N,C,H,W] contiguous (first C channels)."""
     _f32(dst, "nhwc_to_nchw.dst")
-    _lib.check(_lib.load().cvb_nhwc_bf16_to_nchw_f32(view(src), _ptr(dst), dst.shape[1], _stream()), "nhwc_to_nchw")
+    _call("nhwc_to_nchw", 1, _nbytes(src, dst), _lib.load().cvb_nhwc_bf16_to_nchw_f32, view(src), _ptr(dst),
+          dst.shape[1], _stream())
     return dst
 
 
 def im2col3x3(src, dst):
     _f32(src, "im2col3x3.src")
-    _lib.check(_lib.load().cvb_im2col3x3_nchw_f32(_ptr(src), src.shape[1], view(dst), _stream()), "im2col3x3")
+    _call("im2col3x3", 1, _nbytes(src, dst), _lib.load().cvb_im2col3x3_nchw_f32, _ptr(src), src.shape[1], view(dst),
+          _stream())
     return dst
 
 
 def zero_view(t):
-    _lib.check(_lib.load().cvb_zero_view(view(t), _stream()), "zero_view")
+    _call("zero_view", 1, _nbytes(t), _lib.load().cvb_zero_view, view(t), _stream())
     return t
 
 
@@ -84,8 +127,8 @@ def pack_weights_fprop(w, taps, cout_pad, cin_pad, out=None):
     cout, cin = w.shape[0], w.shape[1]
     if out is None:
         out = torch.empty(cout_pad, taps * cin_pad, dtype=torch.bfloat16, device=w.device)
-    _lib.check(_lib.load().cvb_pack_weights_fprop(_ptr(w), cout, cin, taps, cout_pad, cin_pad, _ptr(out), _stream()),
-               "pack_weights_fprop")
+    _call("pack_weights_fprop", 1, _nbytes(w, out), _lib.load().cvb_pack_weights_fprop, _ptr(w), cout, cin, taps,
+          cout_pad, cin_pad, _ptr(out), _stream())
     return out
 
 
@@ -95,13 +138,14 @@ def pack_weights_dgrad(w, cout_pad, cin_pad, out=None):
     cout, cin = w.shape[0], w.shape[1]
     if out is None:
         out = torch.empty(cin_pad, 9 * cout_pad, dtype=torch.bfloat16, device=w.device)
-    _lib.check(_lib.load().cvb_pack_weights_dgrad(_ptr(w), cout, cin, cout_pad, cin_pad, _ptr(out), _stream()),
-               "pack_weights_dgrad")
+    _call("pack_weights_dgrad", 1, _nbytes(w, out), _lib.load().cvb_pack_weights_dgrad, _ptr(w), cout, cin, cout_pad,
+          cin_pad, _ptr(out), _stream())
     return out
 
 
-def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False):
-    """y = conv(x, wpack). Optional epilogues: BN statistics partials (train) or folded scale/shift(+ReLU) (eval)."""
+def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False, algo_flops=None):
+    """y = conv(x, wpack). Optional epilogues: BN statistics partials (train) or folded scale/shift(+ReLU) (eval).
+    algo_flops: FLOPs of the un-padded convolution (roofline accounting); default = the padded GEMM's."""
     ep = ConvEpilogue(stat_partials.data_ptr() if stat_partials is not None else None,
                       scale.data_ptr() if scale is not None else None,
                       shift.data_ptr() if shift is not None else None, 1 if relu else 0)
@@ -109,8 +153,10 @@ def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, rel
         _f32(stat_partials, "conv3x3.stat_partials")
         if stat_partials.numel() < stat_rows() * 2 * y.shape[3]:
             raise RuntimeError("conv3x3: stat_partials too small")
-    _lib.check(_lib.load().cvb_conv3x3_fprop(view(x), _ptr(wpack), taps, view(y), ctypes.byref(ep), _stream()),
-               "conv3x3_fprop")
+    if algo_flops is None:
+        algo_flops = 2.0 * taps * x.shape[3] * y.shape[3] * y.shape[0] * y.shape[1] * y.shape[2]
+    _call("conv3x3_fprop", 1, ("flops", algo_flops), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
+          view(y), ctypes.byref(ep), _stream())
     return y
 
 
@@ -121,80 +167,85 @@ def conv3x3_wgrad_workspace_bytes(x, dy, taps=9):
     return int(r)
 
 
-def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None):
+def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None, algo_flops=None):
     """dw (fp32 OIHW [cout,cin,3,3], overwritten) = weight gradient from activations x and output gradient dy."""
     _f32(dw, "conv3x3_wgrad.dw")
     cout, cin = dw.shape[0], dw.shape[1]
-    need = conv3x3_wgrad_workspace_bytes(x, dy, taps)
     if workspace is None:
-        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
-    _lib.check(_lib.load().cvb_conv3x3_wgrad(view(x), view(dy), taps, _ptr(dw), cout, cin, _ptr(workspace),
-                                             workspace.numel() * workspace.element_size(), _stream()),
-               "conv3x3_wgrad")
+        workspace = torch.empty(conv3x3_wgrad_workspace_bytes(x, dy, taps), dtype=torch.uint8, device=x.device)
+    if algo_flops is None:
+        algo_flops = 2.0 * taps * x.shape[3] * dy.shape[3] * dy.shape[0] * dy.shape[1] * dy.shape[2]
+    _call("conv3x3_wgrad", 2, ("flops", algo_flops), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
+          cout, cin, _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     return dw
 
 
 # ---------------------------------------------------------------- batch norm (+ReLU)
 def bn_stats(y, partials, rows):
-    _lib.check(_lib.load().cvb_bn_stats(view(y), _ptr(partials), rows, _stream()), "bn_stats")
+    _call("bn_stats", 1, _nbytes(y), _lib.load().cvb_bn_stats, view(y), _ptr(partials), rows, _stream())
     return partials
 
 
 def bn_finalize(partials, rows, c, c_pad, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps,
                 mean, invstd, scale, shift):
-    _lib.check(_lib.load().cvb_bn_finalize(_ptr(partials), rows, c, c_pad, count, _ptr(gamma), _ptr(beta),
-                                           _ptr(conv_bias), _ptr(running_mean), _ptr(running_var), momentum, eps,
-                                           _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _stream()),
-               "bn_finalize")
+    _call("bn_finalize", 1, ("bytes", rows * 2 * c_pad * 4.0), _lib.load().cvb_bn_finalize, _ptr(partials), rows, c,
+          c_pad, count, _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean), _ptr(running_var), momentum,
+          eps, _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _stream())
 
 
 def bn_relu_apply(y, scale, shift, a):
-    _lib.check(_lib.load().cvb_bn_relu_apply(view(y), _ptr(scale), _ptr(shift), view(a), _stream()), "bn_relu_apply")
+    _call("bn_relu_apply", 1, _nbytes(y, a), _lib.load().cvb_bn_relu_apply, view(y), _ptr(scale), _ptr(shift),
+          view(a), _stream())
     return a
 
 
 def bn_relu_bwd_reduce(da, y, scale, shift, partials, rows):
-    _lib.check(_lib.load().cvb_bn_relu_bwd_reduce(view(da), view(y), _ptr(scale), _ptr(shift), _ptr(partials), rows,
-                                                  _stream()), "bn_relu_bwd_reduce")
+    _call("bn_relu_bwd_reduce", 1, _nbytes(da, y), _lib.load().cvb_bn_relu_bwd_reduce, view(da), view(y), _ptr(scale),
+          _ptr(shift), _ptr(partials), rows, _stream())
 
 
 def bn_bwd_finalize(partials, rows, c, c_pad, count, gamma, mean, invstd, dgamma, dbeta, coef):
-    _lib.check(_lib.load().cvb_bn_bwd_finalize(_ptr(partials), rows, c, c_pad, count, _ptr(gamma), _ptr(mean),
-                                               _ptr(invstd), _ptr(dgamma), _ptr(dbeta), _ptr(coef), _stream()),
-               "bn_bwd_finalize")
+    _call("bn_bwd_finalize", 1, ("bytes", rows * 2 * c_pad * 4.0), _lib.load().cvb_bn_bwd_finalize, _ptr(partials),
+          rows, c, c_pad, count, _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta), _ptr(coef),
+          _stream())
 
 
 def bn_relu_bwd_apply(da, y, scale, shift, coef, dy):
-    _lib.check(_lib.load().cvb_bn_relu_bwd_apply(view(da), view(y), _ptr(scale), _ptr(shift), _ptr(coef), view(dy),
-                                                 _stream()), "bn_relu_bwd_apply")
+    _call("bn_relu_bwd_apply", 1, _nbytes(da, y, dy), _lib.load().cvb_bn_relu_bwd_apply, view(da), view(y),
+          _ptr(scale), _ptr(shift), _ptr(coef), view(dy), _stream())
     return dy
 
 
 # ---------------------------------------------------------------- pooling
 def maxpool2x2(x, out, code=None):
-    _lib.check(_lib.load().cvb_maxpool2x2_fwd(view(x), view(out), _ptr(code), _stream()), "maxpool2x2_fwd")
+    _call("maxpool2x2_fwd", 1, _nbytes(x, out, code), _lib.load().cvb_maxpool2x2_fwd, view(x), view(out), _ptr(code),
+          _stream())
     return out
 
 
 def bn_relu_maxpool2x2(y, scale, shift, a, out, code=None):
-    _lib.check(_lib.load().cvb_bn_relu_maxpool2x2_fwd(view(y), _ptr(scale), _ptr(shift), view(a), view(out),
-                                                      _ptr(code), _stream()), "bn_relu_maxpool2x2_fwd")
+    _call("bn_relu_maxpool2x2_fwd", 1, _nbytes(y, a, out, code), _lib.load().cvb_bn_relu_maxpool2x2_fwd, view(y),
+          _ptr(scale), _ptr(shift), view(a), view(out), _ptr(code), _stream())
     return out
 
 
 def maxpool2x2_bwd(dout, dx, code=None, x=None, accumulate=False):
-    _lib.check(_lib.load().cvb_maxpool2x2_bwd(view(dout), _ptr(code), view(x), view(dx), 1 if accumulate else 0,
-                                              _stream()), "maxpool2x2_bwd")
+    _call("maxpool2x2_bwd", 1, _nbytes(dout, dx, code, x, dx if accumulate else None),
+          _lib.load().cvb_maxpool2x2_bwd, view(dout), _ptr(code), view(x), view(dx), 1 if accumulate else 0,
+          _stream())
     return dx
 
 
 def maxunpool2x2(x, code, out):
-    _lib.check(_lib.load().cvb_maxunpool2x2_fwd(view(x), _ptr(code), view(out), _stream()), "maxunpool2x2_fwd")
+    _call("maxunpool2x2_fwd", 1, _nbytes(x, code, out), _lib.load().cvb_maxunpool2x2_fwd, view(x), _ptr(code),
+          view(out), _stream())
     return out
 
 
 def maxunpool2x2_bwd(dout, code, dx):
-    _lib.check(_lib.load().cvb_maxunpool2x2_bwd(view(dout), _ptr(code), view(dx), _stream()), "maxunpool2x2_bwd")
+    # reads one of the four window positions per output element: a quarter of dout is touched algorithmically
+    _call("maxunpool2x2_bwd", 1, _nbytes(dx, dx, code), _lib.load().cvb_maxunpool2x2_bwd, view(dout), _ptr(code),
+          view(dx), _stream())
     return dx
 
 
@@ -202,19 +253,19 @@ def pool_code_to_index(code, w_in):
     """uint8 codes [N,Ho,Wo,C] -> torch-style int64 indices [N,C,Ho,Wo] (h*W_in + w per plane)."""
     n, ho, wo, c = code.shape
     idx = torch.empty(n, c, ho, wo, dtype=torch.int64, device=code.device)
-    _lib.check(_lib.load().cvb_pool_code_to_index(_ptr(code), n, ho, wo, c, w_in, _ptr(idx), _stream()),
-               "pool_code_to_index")
+    _call("pool_code_to_index", 1, _nbytes(code, idx), _lib.load().cvb_pool_code_to_index, _ptr(code), n, ho, wo, c,
+          w_in, _ptr(idx), _stream())
     return idx
 
 
 # ---------------------------------------------------------------- upsample
 def bilinear2x(x, out):
-    _lib.check(_lib.load().cvb_bilinear2x_fwd(view(x), view(out), _stream()), "bilinear2x_fwd")
+    _call("bilinear2x_fwd", 1, _nbytes(x, out), _lib.load().cvb_bilinear2x_fwd, view(x), view(out), _stream())
     return out
 
 
 def bilinear2x_bwd(dout, dx):
-    _lib.check(_lib.load().cvb_bilinear2x_bwd(view(dout), view(dx), _stream()), "bilinear2x_bwd")
+    _call("bilinear2x_bwd", 1, _nbytes(dout, dx), _lib.load().cvb_bilinear2x_bwd, view(dout), view(dx), _stream())
     return dx
 
 
@@ -222,15 +273,16 @@ def bilinear2x_bwd(dout, dx):
 def softmax_ce_nchw(logits, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
     _f32(logits, "softmax_ce.logits")
     n, c, h, w = logits.shape
-    _lib.check(_lib.load().cvb_softmax_ce_nchw_f32(_ptr(logits), _ptr(target), n, c, h, w, ignore_index,
-                                                   _ptr(loss_sum_count), _ptr(dlogits), grad_scale,
-                                                   _ptr(grad_scale_dev), _stream()), "softmax_ce_nchw_f32")
+    _call("softmax_ce_nchw_f32", 1, _nbytes(logits, target, dlogits), _lib.load().cvb_softmax_ce_nchw_f32,
+          _ptr(logits), _ptr(target), n, c, h, w, ignore_index, _ptr(loss_sum_count), _ptr(dlogits), grad_scale,
+          _ptr(grad_scale_dev), _stream())
 
 
 def softmax_ce_nhwc(logits, c, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
-    _lib.check(_lib.load().cvb_softmax_ce_nhwc_bf16(view(logits), c, _ptr(target), ignore_index, _ptr(loss_sum_count),
-                                                    view(dlogits), grad_scale, _ptr(grad_scale_dev), _stream()),
-               "softmax_ce_nhwc_bf16")
+    px = logits.shape[0] * logits.shape[1] * logits.shape[2]
+    _call("softmax_ce_nhwc_bf16", 1, ("bytes", px * (c * 2 * (2 if dlogits is not None else 1) + 8.0)),
+          _lib.load().cvb_softmax_ce_nhwc_bf16, view(logits), c, _ptr(target), ignore_index, _ptr(loss_sum_count),
+          view(dlogits), grad_scale, _ptr(grad_scale_dev), _stream())
 
 
 NO_IGNORE = -(2 ** 62)
@@ -243,20 +295,21 @@ def confusion_matrix(pred, gt, c, cm, ignore_label=NO_IGNORE, clamp_oob=False):
             raise RuntimeError(f"confusion_matrix.{nm}: expected a contiguous CUDA int64 tensor")
     if pred.numel() != gt.numel():
         raise RuntimeError("confusion_matrix: pred and gt sizes differ")
-    _lib.check(_lib.load().cvb_confusion_matrix(_ptr(pred), _ptr(gt), pred.numel(), c, ignore_label,
-                                                1 if clamp_oob else 0, _ptr(cm), _stream()), "confusion_matrix")
+    _call("confusion_matrix", 1, _nbytes(pred, gt), _lib.load().cvb_confusion_matrix, _ptr(pred), _ptr(gt),
+          pred.numel(), c, ignore_label, 1 if clamp_oob else 0, _ptr(cm), _stream())
     return cm
 
 
 def argmax_confusion_nchw(logits, gt, cm, pred=None):
     _f32(logits, "argmax_confusion.logits")
     n, c, h, w = logits.shape
-    _lib.check(_lib.load().cvb_argmax_confusion_nchw_f32(_ptr(logits), _ptr(gt), n, c, h, w, _ptr(pred), _ptr(cm),
-                                                         _stream()), "argmax_confusion_nchw_f32")
+    _call("argmax_confusion_nchw_f32", 1, _nbytes(logits, gt, pred), _lib.load().cvb_argmax_confusion_nchw_f32,
+          _ptr(logits), _ptr(gt), n, c, h, w, _ptr(pred), _ptr(cm), _stream())
     return cm
 
 
 def argmax_confusion_nhwc(logits, c, gt, cm, pred=None):
-    _lib.check(_lib.load().cvb_argmax_confusion_nhwc_bf16(view(logits), c, _ptr(gt), _ptr(pred), _ptr(cm), _stream()),
-               "argmax_confusion_nhwc_bf16")
+    px = logits.shape[0] * logits.shape[1] * logits.shape[2]
+    _call("argmax_confusion_nhwc_bf16", 1, ("bytes", px * (c * 2 + 8.0 + (8.0 if pred is not None else 0.0))),
+          _lib.load().cvb_argmax_confusion_nhwc_bf16, view(logits), c, _ptr(gt), _ptr(pred), _ptr(cm), _stream())
     return cm
