@@ -155,7 +155,7 @@ def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, rel
             raise RuntimeError("conv3x3: stat_partials too small")
     if algo_flops is None:
         algo_flops = 2.0 * taps * x.shape[3] * y.shape[3] * y.shape[0] * y.shape[1] * y.shape[2]
-    _call("conv3x3_fprop", 1, ("flops", algo_flops), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
+    _call("conv3x3_fprop", 1, ("flops", algo_flops, f"{tuple(x.shape)}->{y.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
           view(y), ctypes.byref(ep), _stream())
     return y
 
@@ -175,7 +175,7 @@ def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None, algo_flops=None):
         workspace = torch.empty(conv3x3_wgrad_workspace_bytes(x, dy, taps), dtype=torch.uint8, device=x.device)
     if algo_flops is None:
         algo_flops = 2.0 * taps * x.shape[3] * dy.shape[3] * dy.shape[0] * dy.shape[1] * dy.shape[2]
-    _call("conv3x3_wgrad", 2, ("flops", algo_flops), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
+    _call("conv3x3_wgrad", 2, ("flops", algo_flops, f"{tuple(x.shape)}->{dy.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
           cout, cin, _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     return dw
 
