@@ -83,26 +83,61 @@ static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finalize kernels: tiny, one thread per channel, double accumulation over the partial rows
+// finalize kernels: a block owns 32 channels; its 8 warps split the partial rows (coalesced 128-byte row reads),
+// accumulate in double and combine through shared memory, then warp 0 finishes the 32 channels.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride,
-                                   double inv_count, double unbias, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ conv_bias,
-                                   float* running_mean, float* running_var, float momentum, float eps, float* mean,
-                                   float* invstd, float* scale, float* shift) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c_pad) return;
+constexpr int kFinThreads = 256;
+
+__device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ partials, int rows, int pstride, int ch,
+                                                    bool ch_ok, double* s1_out, double* s2_out) {
+  __shared__ double sh[2][8][32];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  double s1 = 0.0, s2 = 0.0;
+  if (ch_ok) {
+    int r = wq;
+    for (; r + 24 < rows; r += 32) {  // 4 independent row loads in flight per thread
+      float a0 = partials[(2LL * r) * pstride + ch], b0 = partials[(2LL * r + 1) * pstride + ch];
+      float a1 = partials[(2LL * (r + 8)) * pstride + ch], b1 = partials[(2LL * (r + 8) + 1) * pstride + ch];
+      float a2 = partials[(2LL * (r + 16)) * pstride + ch], b2 = partials[(2LL * (r + 16) + 1) * pstride + ch];
+      float a3 = partials[(2LL * (r + 24)) * pstride + ch], b3 = partials[(2LL * (r + 24) + 1) * pstride + ch];
+      s1 += (static_cast<double>(a0) + a1) + (static_cast<double>(a2) + a3);
+      s2 += (static_cast<double>(b0) + b1) + (static_cast<double>(b2) + b3);
+    }
+    for (; r < rows; r += 8) {
+      s1 += static_cast<double>(partials[(2LL * r) * pstride + ch]);
+      s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
+    }
+  }
+  sh[0][wq][lane] = s1;
+  sh[1][wq][lane] = s2;
+  __syncthreads();
+  if (wq == 0) {
+    s1 = s2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s1 += sh[0][q][lane];
+      s2 += sh[1][q][lane];
+    }
+  }
+  *s1_out = s1;
+  *s2_out = s2;
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+bn_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride, double inv_count,
+                   double unbias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ conv_bias, float* running_mean, float* running_var, float momentum,
+                   float eps, float* mean, float* invstd, float* scale, float* shift) {
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s1, s2;
+  reduce_partial_rows(partials, rows, pstride, ch, ch < c, &s1, &s2);
+  if (threadIdx.x >= 32 || ch >= c_pad) return;
   if (ch >= c) {
     scale[ch] = 0.f;
     shift[ch] = 0.f;
     if (mean) mean[ch] = 0.f;
     if (invstd) invstd[ch] = 0.f;
     return;
-  }
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s1 += static_cast<double>(partials[(2LL * r) * pstride + ch]);
-    s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
   }
   double m = s1 * inv_count;
   double var = s2 * inv_count - m * m;
@@ -120,22 +155,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int rows,
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride,
-                                       double inv_count, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                       float* dgamma, float* dbeta, float* coef) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c_pad) return;
+__global__ void __launch_bounds__(kFinThreads)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride, double inv_count,
+                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  double sg, sgy;
+  reduce_partial_rows(partials, rows, pstride, ch, ch < c, &sg, &sgy);
+  if (threadIdx.x >= 32 || ch >= c_pad) return;
   if (ch >= c) {
     coef[ch] = 0.f;
     coef[c_pad + ch] = 0.f;
     coef[2 * c_pad + ch] = 0.f;
     return;
-  }
-  double sg = 0.0, sgy = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    sg += static_cast<double>(partials[(2LL * r) * pstride + ch]);
-    sgy += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
   }
   double m = mean[ch], is = invstd[ch], g = gamma[ch];
   double dg = is * (sgy - m * sg);  // sum g * xhat
@@ -249,7 +281,7 @@ extern "C" int cvb_bn_finalize(const float* partials, int rows, int c, int c_pad
               "bn_finalize: running_mean and running_var must both be given or both be NULL");
   double inv = 1.0 / static_cast<double>(count);
   double unbias = count > 1 ? static_cast<double>(count) / static_cast<double>(count - 1) : 1.0;
-  bn_finalize_kernel<<<(c_pad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(c_pad + 31) / 32, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, c, c_pad, c_pad, inv, unbias, gamma, beta, conv_bias, running_mean, running_var, momentum, eps,
       mean, invstd, scale, shift);
   CVB_LAUNCH_CHECK();
@@ -262,7 +294,7 @@ extern "C" int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c
   CVB_REQUIRE(partials && gamma && mean && invstd && dgamma && dbeta && coef, CVB_ERR_INVALID_ARG,
               "bn_bwd_finalize: null pointer");
   CVB_REQUIRE(rows > 0 && c > 0 && c_pad >= c && count > 0, CVB_ERR_INVALID_ARG, "bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<(c_pad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_bwd_finalize_kernel<<<(c_pad + 31) / 32, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, c, c_pad, c_pad, 1.0 / static_cast<double>(count), gamma, mean, invstd, dgamma, dbeta, coef);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

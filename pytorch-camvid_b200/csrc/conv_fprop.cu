@@ -12,6 +12,8 @@
 //   * persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
 //     allocator, warps 4-7 = epilogue (TMEM -> registers -> bf16 NHWC stores, plus per-channel sum / sum-of-squares
 //     for the BatchNorm batch statistics, or the folded eval-mode BN+ReLU).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tma_host.h"
@@ -30,11 +32,13 @@ struct FpropParams {
   const float* scale;
   const float* shift;
   int relu;
+  int debug;  // development knobs (CVB_DEBUG env): bit 0 = skip the output stores, bit 1 = MMA-thread wait trace
+  long long* trace;  // with debug bit 1: the stat_partials buffer reinterpreted (statistics are then not produced)
 };
 
 constexpr int kFpropThreads = 256;
 constexpr int kABytes = 128 * 128;  // 128 pixel rows x 64 bf16
-constexpr int kStatFloats = 2 * 1024;
+constexpr int kStatFloats = 4 * 2 * 1024;  // one private [sum | sumsq][cout_pad <= 1024] row per epilogue warp
 
 template <int BN>
 struct FpropCfg {
@@ -81,6 +85,82 @@ __device__ __forceinline__ float warp_column_sum(float (&v)[32], int lane) {
     v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
   }
   return v[0];
+}
+
+// 32 accumulator columns of one output pixel: (eval: folded BatchNorm + ReLU) -> bf16 -> four 16-byte stores.
+__device__ __forceinline__ void epilogue_store(const FpropParams& p, const uint32_t (&r)[32], __nv_bfloat16* dst, int ch,
+                                               bool valid) {
+  if (!valid || (p.debug & 1)) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.scale) {
+    const float* sc = p.scale + ch;
+    const float* sh = p.shift + ch;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = fmaf(v[j], __ldg(sc + j), __ldg(sh + j));
+      if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(dst + q * 8) = o;
+  }
+}
+
+// Epilogue of one 32-row slab of an accumulator tile: TMEM -> registers -> (eval: folded BN + ReLU) -> bf16 NHWC store,
+// plus per-channel sum / sum of squares of the fp32 accumulators for the BatchNorm batch statistics (train).
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const FpropParams& p, uint32_t taddr, __nv_bfloat16* dst, int ch0,
+                                              bool valid, int lane, float* s_stats) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c0, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.scale) {
+      const float* sc = p.scale + ch0 + c0;
+      const float* sh = p.shift + ch0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = fmaf(v[j], __ldg(sc + j), __ldg(sh + j));
+        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+      }
+    }
+    if (valid && !(p.debug & 1)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+        o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+        o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+        o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + c0 + q * 8) = o;
+      }
+    }
+    if (p.stat_partials) {
+      float sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = valid ? v[j] : 0.f;
+        sq[j] = v[j] * v[j];
+      }
+      float s1 = warp_column_sum(v, lane);
+      float s2 = warp_column_sum(sq, lane);
+      // s_stats is this warp's private row and a lane always owns the same columns: plain read-modify-write
+      s_stats[ch0 + c0 + lane] += s1;
+      s_stats[p.cout_pad + ch0 + c0 + lane] += s2;
+    }
+  }
 }
 
 template <int BN>
@@ -158,36 +238,38 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------- MMA issuer ---------------------------------
-      constexpr uint32_t idesc = idesc_bf16_f32(128, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, false, false);
+    constexpr uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * BN;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(d, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+        const uint32_t a_lo = a_lo0 + stage * (kABytes >> 4), b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
+        if (elect_one()) {
+          umma_bf16_lohi(d, a_lo, hi, b_lo, hi, idesc, kb != 0 ? 1u : 0u);
+          umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+          umma_bf16_lohi(d, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+          umma_bf16_lohi(d, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
           umma_commit(&empty[stage]);
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // --------------------------------- epilogue -----------------------------------
@@ -213,47 +295,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __nv_bfloat16* dst = p.y + n * p.ysn + h * p.ysh + w * p.ysw + nt * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c0, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.scale) {
-          const float* sc = p.scale + nt * BN + c0;
-          const float* sh = p.shift + nt * BN + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = fmaf(v[j], __ldg(sc + j), __ldg(sh + j));
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-          }
-        }
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(dst + c0 + q * 8) = o;
-          }
-        }
-        if (p.stat_partials) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = valid ? v[j] : 0.f;
-            sq[j] = v[j] * v[j];
-          }
-          float s1 = warp_column_sum(v, lane);
-          float s2 = warp_column_sum(sq, lane);
-          atomicAdd(&s_stats[nt * BN + c0 + lane], s1);
-          atomicAdd(&s_stats[p.cout_pad + nt * BN + c0 + lane], s2);
-        }
-      }
+      epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, dst, nt * BN, valid, lane,
+                        s_stats + ew * 2 * p.cout_pad);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -265,7 +308,272 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (p.stat_partials) {
     float* dstp = p.stat_partials + static_cast<long long>(blockIdx.x) * 2 * p.cout_pad;
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kFpropThreads) dstp[i] = s_stats[i];
+    const int n2 = 2 * p.cout_pad;
+    for (int i = threadIdx.x; i < n2; i += kFpropThreads)
+      dstp[i] = (s_stats[i] + s_stats[n2 + i]) + (s_stats[2 * n2 + i] + s_stats[3 * n2 + i]);
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Halo variant for the wide-and-shallow layers (cout_pad <= 128: the full- and half-resolution stages).  There the
+// kernel above is bound by L2 -> shared-memory traffic, not by the tensor pipe: every tap re-fetches the (shifted)
+// activation tile and every 128-pixel tile re-fetches the weights.  Here
+//   * a CTA tile is 8 (w) x 32 (h) pixels = two 128-row accumulators; its activation patch (10 x 34 pixels x 64
+//     channels, zero-filled by TMA outside the image) is fetched ONCE per 64-channel chunk;
+//   * the nine taps are nine shifted views of that patch: the tcgen05 shared-memory descriptor starts at patch row
+//     ((dr+1)*10 + ds+1) and strides 10 rows (1280 B) between 8-pixel groups -- the 128-byte swizzle is a function of
+//     the absolute shared-memory address, so a start that is not 1024-byte aligned addresses the same data TMA wrote
+//     (verified on B200: tools/exp/exp_desc.cu);
+//   * each weight tile (tap, chunk) is fetched once per CTA tile and used by both accumulators.
+// L2 -> smem bytes per 128x64x576 MMA block drop from 216 KB to 58 KB (BN = 64).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHaloW = 8, kHaloH = 32;
+constexpr int kHaloThreads = 384;  // 4 control warps + 8 epilogue warps (4 per accumulator half)
+constexpr int kPatchRows = (kHaloH + 2) * (kHaloW + 2);  // 340 pixel rows of 128 B
+constexpr int kPatchBytes = kPatchRows * 128;             // 43520
+constexpr int kPatchStride = 45056;                       // rounded up to 1 KB
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int kStagesA = 3;
+  static constexpr int kStagesB = BN == 64 ? 8 : 5;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kTmemCols = 4 * BN;  // 2 halves x double buffering
+  static constexpr int kSmem = 1024 + kStagesA * kPatchStride + kStagesB * kBBytes + 4 * 2 * BN * 4 + 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_fprop_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const FpropParams p) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * kPatchStride;
+  float* s_stats = reinterpret_cast<float*>(sB + SB * Cfg::kBBytes);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(s_stats + 4 * 2 * BN);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tfull = emptyB + SB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&fullA[i], 1);
+      mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(&fullB[i], 1);
+      mbar_init(&emptyB[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // 384 threads x 168 registers at launch; the four control warps give registers back, the eight epilogue warps take
+  // them (64 or 128 private statistic accumulators each)
+  // (setmaxnreg sits inside the role branches: placed before them, ptxas applies the smaller bound to every role)
+  if (warp < 4) {
+  setmaxnreg_dec<40>();
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- activation-patch producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int mt = tile;
+        const int w0 = (mt % p.tiles_w) * kHaloW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * kHaloH;
+        const int n0 = mt / p.tiles_h;
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          mbar_wait(&emptyA[stage], phase ^ 1);
+          mbar_expect_tx(&fullA[stage], kPatchBytes);
+          tma_load_4d(sA + stage * kPatchStride, &tmA, &fullA[stage], chunk * 64, w0 - 1, h0 - 1, n0);
+          if (++stage == SA) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------- weight-tile producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyB[stage], phase ^ 1);
+            mbar_expect_tx(&fullB[stage], Cfg::kBBytes);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &fullB[stage], tap * p.cin_pad + chunk * 64, 0);
+            if (++stage == SB) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, false, false);
+    constexpr uint32_t a_hi = desc_hi_sw128((kHaloW + 2) * 128), b_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kHaloH;
+      const bool two = h0 + 16 < p.H;  // lower half entirely below the image: skip its MMAs
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * 2 * BN;
+      for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+        mbar_wait(&fullA[sa], pa);
+        const uint32_t a_st = a_lo0 + sa * (kPatchStride >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&fullB[sb], pb);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + sb * (Cfg::kBBytes >> 4);
+          const int dr = tap / 3, ds = tap - dr * 3;  // already offset by +1 (patch origin is (h0-1, w0-1))
+          const uint32_t a_lo = a_st + (dr * (kHaloW + 2) + ds) * 8;  // 128-byte rows in 16-byte units
+          const uint32_t first = (chunk | tap) != 0 ? 1u : 0u;
+          if (elect_one()) {
+            umma_bf16_lohi(d0, a_lo, a_hi, b_lo, b_hi, idesc, first);
+            umma_bf16_lohi(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+            umma_bf16_lohi(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+            umma_bf16_lohi(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            if (two) {
+              constexpr uint32_t half = 16 * (kHaloW + 2) * 8;
+              umma_bf16_lohi(d0 + BN, a_lo + half, a_hi, b_lo, b_hi, idesc, first);
+              umma_bf16_lohi(d0 + BN, a_lo + half + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              umma_bf16_lohi(d0 + BN, a_lo + half + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_bf16_lohi(d0 + BN, a_lo + half + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            }
+            umma_commit(&emptyB[sb]);
+          }
+          __syncwarp();
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&emptyA[sa]);
+        __syncwarp();
+        if (++sa == SA) {
+          sa = 0;
+          pa ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  }
+  } else {
+    setmaxnreg_inc<232>();
+    // --------------------------------- epilogue -----------------------------------
+    // Warps 4-7 own output channels [0, BN/2), warps 8-11 [BN/2, BN), of BOTH accumulator halves; a warp reads the TMEM
+    // lane quadrant warp % 4, i.e. tile rows ew*4 .. ew*4+3 of each half. BatchNorm statistics: every thread keeps a
+    // private running sum / sum of squares per channel it sees (its pixel changes from tile to tile, its channels never
+    // do), so the cross-lane reduction happens ONCE per kernel instead of once per tile -- per tile the statistics cost
+    // one FADD + one FFMA per element (the shuffle-based per-tile reduction was ~10x that and issue-bound).
+    constexpr int CH = BN / 2;  // channels per warp
+    const int ew = warp & 3;
+    const int cbase = ((warp - 4) >> 2) * CH;
+    const int row = ew * 32 + lane;
+    const int ty_ = row >> 3, tx_ = row & 7;
+    float S[CH], Q[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) S[j] = Q[j] = 0.f;
+    const bool want_stats = p.stat_partials != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int mt = tile;
+      const int w = (mt % p.tiles_w) * kHaloW + tx_;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * kHaloH;
+      const int n = mt / p.tiles_h;
+      const int halves = (h0 + 16 < p.H) ? 2 : 1;  // the MMA warp skips a lower half that lies below the image
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int half = 0; half < halves; ++half) {
+        const int h = h0 + half * 16 + ty_;
+        const bool valid = h < p.H && w < p.W;
+        __nv_bfloat16* dst = p.y + n * p.ysn + h * p.ysh + w * p.ysw + cbase;
+        const uint32_t t_a = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * 2 + half) * BN + cbase;
+#pragma unroll
+        for (int c = 0; c < CH / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_a + c * 32, r);
+          tmem_ld_wait();
+          epilogue_store(p, r, dst + c * 32, cbase + c * 32, valid);
+          if (want_stats && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              S[c * 32 + j] += v;
+              Q[c * 32 + j] = fmaf(v, v, Q[c * 32 + j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    // one cross-lane reduction per kernel; s_stats[warp quadrant][sum | sumsq][BN]
+#pragma unroll
+    for (int c = 0; c < CH / 32; ++c) {
+      float s[32], q[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s[j] = S[c * 32 + j];
+        q[j] = Q[c * 32 + j];
+      }
+      const float s1 = warp_column_sum(s, lane), s2 = warp_column_sum(q, lane);
+      s_stats[ew * 2 * BN + cbase + c * 32 + lane] = s1;
+      s_stats[ew * 2 * BN + BN + cbase + c * 32 + lane] = s2;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (p.stat_partials) {
+    float* dstp = p.stat_partials + static_cast<long long>(blockIdx.x) * 2 * p.cout_pad;
+    for (int i = threadIdx.x; i < 2 * BN; i += kHaloThreads)
+      dstp[i] = (s_stats[i] + s_stats[2 * BN + i]) + (s_stats[4 * BN + i] + s_stats[6 * BN + i]);
   }
   if (warp == 2) {
     tc_fence_after();
@@ -323,6 +631,19 @@ static int launch_fprop(const CUtensorMap& tmA, const CUtensorMap& tmB, const Fp
   return CVB_OK;
 }
 
+template <int BN>
+static int launch_fprop_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = HaloCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(conv_fprop_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  conv_fprop_halo_kernel<BN><<<sm_count(), kHaloThreads, Cfg::kSmem, st>>>(tmA, tmB, p);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -358,10 +679,19 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   CVB_REQUIRE(total < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_fprop: too many tiles");
   p.total_tiles = static_cast<int>(total);
   p.a_bytes = static_cast<uint32_t>(p.TW * p.TH * p.TN) * 128u;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("CVB_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+    if ((dbg & 2) && ep && ep->stat_partials) p.trace = reinterpret_cast<long long*>(ep->stat_partials);
+  }
   p.y = static_cast<__nv_bfloat16*>(y.ptr);
   p.ysn = y.sn; p.ysh = y.sh; p.ysw = y.sw;
   if (ep) {
-    p.stat_partials = ep->stat_partials;
+    p.stat_partials = (p.debug & 2) ? nullptr : ep->stat_partials;
     p.scale = ep->scale;
     p.shift = ep->shift;
     p.relu = ep->relu;
@@ -369,11 +699,25 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
                 "conv_fprop: scale and shift must both be given or both be NULL");
   }
   CUtensorMap tmA, tmB;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (taps == 9 && y.c <= 128 && x.w >= kHaloW && x.h >= 16) {
+    // wide-and-shallow layer: halo kernel (one patch fetch per chunk, nine shifted descriptor views)
+    p.TW = kHaloW; p.TH = kHaloH; p.TN = 1;
+    p.tiles_w = (x.w + kHaloW - 1) / kHaloW;
+    p.tiles_h = (x.h + kHaloH - 1) / kHaloH;
+    p.tiles_n = x.n;
+    p.n_tiles = 1;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    rc = make_act_tmap(&tmA, x, kHaloW + 2, kHaloH + 2, 1);
+    if (rc) return rc;
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, y.c);
+    if (rc) return rc;
+    return y.c == 64 ? launch_fprop_halo<64>(tmA, tmB, p, st) : launch_fprop_halo<128>(tmA, tmB, p, st);
+  }
   rc = make_act_tmap(&tmA, x, p.TW, p.TH, p.TN);
   if (rc) return rc;
   rc = make_mat_tmap(&tmB, wpack, y.c, 1LL * taps * x.c, BN);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (BN) {
     case 256: return launch_fprop<256>(tmA, tmB, p, st);
     case 128: return launch_fprop<128>(tmA, tmB, p, st);

@@ -28,6 +28,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Warp-group register reallocation (all four warps of an aligned warp group must execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
@@ -118,6 +128,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Lean issue path: the 64-bit shared-memory descriptor is passed as two 32-bit halves so that the per-MMA address
+// arithmetic is ONE 32-bit add on the low word (k-step of 32 B = +2; tap / stage offsets likewise), the high word
+// (SBO, version, swizzle) is a compile-time constant, and the whole thing stays in uniform registers. The MMA warp
+// runs its control flow warp-uniformly and issues under elect_one(): with `if (lane == 0)` ptxas cannot prove that a
+// single thread is active and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (~75-130 issue cycles per MMA,
+// measured), which is slower than the MMA itself for N <= 128.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // All previously issued MMAs of this thread arrive on `bar` when they retire (implies fence::before).
