@@ -4,15 +4,19 @@
 //
 //   dW[co][ci][tap] = sum over pixels p of  dy[p][co] * x[p + tap offset][ci]
 //
-// GEMM view (K = pixels): D_tap[M = ci][N = co] = X_tap^T * dY.  Both operands are "MN-major": the TMA box
-// [64 pixels][64 channels] lands as 64 rows of 128 B (128B swizzle) and tcgen05 reads it transposed, so no
+// GEMM view (K = pixels): D_tap[M = ci][N = co] = X_tap^T * dY.  Both operands are "MN-major": a pixel is one 128-byte
+// shared-memory row of 64 channels (128B swizzle, exactly what TMA writes) and tcgen05 reads it transposed, so no
 // transposed copy of the activations is ever materialised.
-//   * "unit"   = one such 8 KB box. x units are fetched with the box shifted by the tap offset (TMA zero-fills outside
-//                the image = the convolution padding); dy units are unshifted and shared by every tap of the item.
-//   * M = 128 = two x units: two 64-channel chunks of one tap (cin >= 128) or two taps of a 64-channel input.
-//   * a CTA owns one work item = (co tile, ci tile, tap group, K split) and keeps one fp32 accumulator per unit pair
-//     in TMEM for its whole pixel range; split-K partials go to a workspace that a second kernel reduces and
-//     transposes to the OIHW fp32 layout of nn.Conv2d.weight.grad (deterministic, no atomics).
+//   * pixel tile = 8 (w) x 16 (h); one K=16 MMA slice = two tile rows of 8 pixels (SBO = row pitch).
+//   * the activation patch of a tile (10 x 18 pixels, halo included, zero-filled by TMA outside the image = the
+//     convolution padding) is fetched ONCE per 64-channel chunk; every tap is a shifted descriptor view of it (start
+//     row (dr*10 + ds), any 128-byte row is a legal start: the swizzle is a function of the absolute smem address,
+//     tools/exp/exp_desc.cu). The dy tile is fetched once and shared by all taps.
+//   * M = 128 = two 64-row atoms: two input-channel chunks of one tap (cin >= 128; LBO = chunk stride in smem) or two
+//     taps of a 64-channel input (LBO = distance between the two tap views).
+//   * a CTA owns one work item = (co tile, ci tile, tap group, K split) and keeps one fp32 accumulator per atom pair
+//     in TMEM for its whole pixel range; split-K partials go to a workspace that a second kernel reduces and transposes
+//     to the OIHW fp32 layout of nn.Conv2d.weight.grad (deterministic, no atomics).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tma_host.h"
@@ -20,30 +24,34 @@
 namespace cvb {
 
 constexpr int kWgradThreads = 256;
-constexpr int kUnitBytes = 64 * 128;
-constexpr int kWgradSmemBudget = 200 * 1024;
+constexpr int kWTileW = 8, kWTileH = 16;
+constexpr int kWPitch = kWTileW + 2;                       // patch row pitch in pixels
+constexpr int kWPatchRows = (kWTileH + 2) * kWPitch;      // 180
+constexpr int kWPatchBytes = kWPatchRows * 128;           // 23040
+constexpr int kWPatchStride = 23552;                      // rounded up to 1 KB
+constexpr int kWDyBytes = kWTileW * kWTileH * 128;        // 16384 per 64-channel unit
+constexpr int kWgradSmemBudget = 225 * 1024;
+constexpr int kMaxAccs = 8;
 
 struct WgradParams {
-  int PW, PH, PN;                 // pixel patch of one K block (PW*PH*PN == 64)
-  int tiles_w, tiles_h, tiles_n;  // patches per image row / column / batch
-  int kt_total;                   // K blocks in the whole tensor
-  int taps;                       // 9 or 1
+  int N, H, W;
+  int tiles_w, tiles_h, total_tiles;
+  int taps;  // 9 or 1
   int cin_pad, cout_pad;
-  int BN, CM, T;                  // co tile, 64-channel ci chunks per tap in M, taps per item
+  int CM, T;  // 64-channel ci chunks per M=128 accumulator (1 or 2), taps per work item
   int n_co_tiles, n_ci_tiles, n_tap_groups, splits;
-  int units_pad;                  // x units per stage, rounded up to even
-  int stages;
-  float* ws;                      // [splits][taps][cin_pad][cout_pad]
+  int stages, stage_bytes;
+  float* ws;  // [splits][taps][cin_pad][cout_pad]
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_units = p.BN / 64;
-  const int stage_bytes = (p.units_pad + b_units) * kUnitBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  constexpr int b_units = BN / 64;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -61,10 +69,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int split = item / p.n_tap_groups;
   const int t0 = tg * p.T;
   const int tcount = min(p.T, p.taps - t0);
-  const int units = tcount * p.CM;
+  const int units = tcount * p.CM;  // 64-row atoms this item accumulates
   const int accs = (units + 1) >> 1;
-  const int kb_begin = static_cast<int>(1LL * p.kt_total * split / p.splits);
-  const int kb_end = static_cast<int>(1LL * p.kt_total * (split + 1) / p.splits);
+  const int tile_begin = static_cast<int>(1LL * p.total_tiles * split / p.splits);
+  const int tile_end = static_cast<int>(1LL * p.total_tiles * (split + 1) / p.splits);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -92,26 +100,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // ------------------------------- TMA producer -------------------------------
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(units + b_units) * kUnitBytes;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        int t = kb;
-        const int pw0 = (t % p.tiles_w) * p.PW;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.CM) * kWPatchBytes + b_units * kWDyBytes;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int t = tile;
+        const int w0 = (t % p.tiles_w) * kWTileW;
         t /= p.tiles_w;
-        const int ph0 = (t % p.tiles_h) * p.PH;
-        const int pn0 = (t / p.tiles_h) * p.PN;
-        uint8_t* sA = smem + stage * stage_bytes;
-        uint8_t* sB = sA + p.units_pad * kUnitBytes;
+        const int h0 = (t % p.tiles_h) * kWTileH;
+        const int n0 = t / p.tiles_h;
+        uint8_t* sX = smem + stage * p.stage_bytes;
+        uint8_t* sD = sX + p.CM * kWPatchStride;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], tx_bytes);
-        for (int u = 0; u < units; ++u) {
-          const int tap = t0 + u / p.CM;
-          const int chunk = ci_tile * p.CM + u % p.CM;
-          const int dr = p.taps == 9 ? tap / 3 - 1 : 0;
-          const int ds = p.taps == 9 ? tap % 3 - 1 : 0;
-          tma_load_4d(sA + u * kUnitBytes, &tmX, &full[stage], chunk * 64, pw0 + ds, ph0 + dr, pn0);
-        }
+        for (int c = 0; c < p.CM; ++c)
+          tma_load_4d(sX + c * kWPatchStride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
+#pragma unroll
         for (int j = 0; j < b_units; ++j)
-          tma_load_4d(sB + j * kUnitBytes, &tmDY, &full[stage], co_tile * p.BN + j * 64, pw0, ph0, pn0);
+          tma_load_4d(sD + j * kWDyBytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -119,61 +123,99 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------- MMA issuer ---------------------------------
-      const uint32_t idesc = idesc_bf16_f32(128, p.BN, true, true);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_base = a_base + p.units_pad * kUnitBytes;
-        for (int j = 0; j < accs; ++j) {
+    // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, true, true);
+    constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive tile rows of the patch
+    constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy tile rows are dense
+    // per accumulator: descriptor low word of its first atom relative to the stage base (row offset of the tap view,
+    // in 16-byte units) with the LBO field = distance to the second atom
+    uint32_t acc_lo[kMaxAccs];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixel rows per MMA = 2 groups of 8 rows (SBO 1024 B); 64-channel atoms are one unit apart (LBO).
-            const uint64_t adesc = smem_desc_sw128(a_base + (2 * j) * kUnitBytes + k * 2048, kUnitBytes, 1024);
-            const uint64_t bdesc = smem_desc_sw128(b_base + k * 2048, kUnitBytes, 1024);
-            umma_bf16(tmem_base + j * p.BN, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
+    for (int j = 0; j < kMaxAccs; ++j) {
+      int tap_a, tap_b;
+      uint32_t lbo;
+      if (p.CM == 2) {
+        tap_a = tap_b = t0 + j;
+        lbo = kWPatchStride;
+      } else {
+        tap_a = t0 + 2 * j;
+        tap_b = tap_a + 1;
+        lbo = 0;
+      }
+      const int ra = p.taps == 9 ? (tap_a / 3) * kWPitch + tap_a % 3 : kWPitch + 1;
+      const int rb = p.taps == 9 ? (tap_b / 3) * kWPitch + tap_b % 3 : kWPitch + 2;
+      if (p.CM != 2) lbo = static_cast<uint32_t>(rb - ra) * 128;  // second atom = the next tap's view (positive)
+      acc_lo[j] = static_cast<uint32_t>(ra) * 8 + ((lbo >> 4) << 16);
+    }
+    const uint32_t x_lo0 = desc_lo(smem_u32(smem), 0);
+    const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * kWPatchStride, kWDyBytes);
+    const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kWTileH;
+      const int rows = min(kWTileH, p.H - h0);
+      const int slices = (rows + 1) >> 1;  // K slices of two tile rows that touch the image
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t x_lo = x_lo0 + stage * stage_lo, d_lo = d_lo0 + stage * stage_lo;
+      const uint32_t first = tile != tile_begin ? 1u : 0u;
+      if (elect_one()) {
+        for (int s = 0; s < slices; ++s) {
+          const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
+          const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < kMaxAccs; ++j)
+            if (j < accs) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
         }
         umma_commit(&empty[stage]);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      umma_commit(tfull);
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+    if (elect_one()) umma_commit(tfull);
+    __syncwarp();
   } else if (warp >= 4) {
-    // --------------------------------- epilogue -----------------------------------
+    // --------------------------------- epilogue (once per CTA) -----------------------------------
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
-    if (kb_end > kb_begin) {
+    const int atom = row >> 6, r = row & 63;
+    const bool has_work = tile_end > tile_begin;
+    if (has_work) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
     for (int j = 0; j < accs; ++j) {
-      const int u = 2 * j + (row >> 6);
-      const bool valid = u < units;
-      const int tap = t0 + u / p.CM;
-      const int ci = (ci_tile * p.CM + u % p.CM) * 64 + (row & 63);
-      float* dst = p.ws + ((static_cast<long long>(split) * p.taps + tap) * p.cin_pad + ci) * p.cout_pad +
-                   co_tile * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t r[32];
-        if (kb_end > kb_begin) {
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + j * p.BN + c0, r);
+      int tap, ci;
+      bool valid;
+      if (p.CM == 2) {
+        tap = t0 + j;
+        ci = (ci_tile * 2 + atom) * 64 + r;
+        valid = true;
+      } else {
+        const int u = 2 * j + atom;
+        valid = u < units;
+        tap = t0 + u;
+        ci = ci_tile * 64 + r;
+      }
+      float* dst = p.ws + ((static_cast<long long>(split) * p.taps + tap) * p.cin_pad + ci) * p.cout_pad + co_tile * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        if (has_work) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + j * BN + c0, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) r[q] = 0;
+          for (int q = 0; q < 32; ++q) v[q] = 0;
         }
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(dst + c0 + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+            *reinterpret_cast<uint4*>(dst + c0 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
       }
     }
@@ -187,42 +229,50 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
-// out[co][ci][tap] = sum_s ws[s][tap][ci][co]; a block transposes a 32(co) x 32(ci) x taps brick through smem so both
-// the workspace reads and the OIHW writes are coalesced.
+// out[co][ci][tap] = sum_s ws[s][tap][ci][co].  A block owns a brick of 32 co x BCI ci x all taps: it sums the splits with
+// coalesced 128-byte reads (co fastest), transposes the brick through shared memory and writes runs of BCI*taps
+// contiguous floats per co row of the OIHW tensor. BCI shrinks for small layers so that the grid still fills the GPU.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps,
-                                                           int cin_pad, int cout_pad, int cout, int cin_eff,
+                                                           int cin_pad, int cout_pad, int cout, int cin_eff, int bci,
                                                            float* __restrict__ out) {
-  extern __shared__ float tile[];  // [taps][32][33]
-  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  extern __shared__ float tile[];  // [taps][bci][33]
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * bci;
+  const int tx = threadIdx.x & 31;
   const long long split_stride = 1LL * taps * cin_pad * cout_pad;
-  for (int tap = 0; tap < taps; ++tap) {
-    for (int i = ty; i < 32; i += 8) {
-      const int ci = ci0 + i, co = co0 + tx;
-      float acc = 0.f;
-      if (ci < cin_pad && co < cout_pad) {
-        const float* src = ws + (1LL * tap * cin_pad + ci) * cout_pad + co;
-        for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+  const int elems = taps * bci;  // (tap, i) pairs, each a 32-wide co row
+  for (int e = threadIdx.x >> 5; e < elems; e += 8) {
+    const int tap = e / bci, i = e - tap * bci;
+    const int ci = ci0 + i, co = co0 + tx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (ci < cin_pad && co < cout_pad) {
+      const float* src = ws + (1LL * tap * cin_pad + ci) * cout_pad + co;
+      int s = 0;
+      for (; s + 3 < splits; s += 4) {  // four independent loads in flight
+        a0 += src[s * split_stride];
+        a1 += src[(s + 1) * split_stride];
+        a2 += src[(s + 2) * split_stride];
+        a3 += src[(s + 3) * split_stride];
       }
-      tile[(tap * 32 + i) * 33 + tx] = acc;
+      for (; s < splits; ++s) a0 += src[s * split_stride];
     }
+    tile[(tap * bci + i) * 33 + tx] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  // write: for each co row, (ci, tap) is contiguous in OIHW
-  const int row_elems = 32 * taps;
-  for (int j = ty; j < 32; j += 8) {
+  const int row_elems = bci * taps;  // contiguous in OIHW for a fixed co
+  for (int j = threadIdx.x >> 5; j < 32; j += 8) {
     const int co = co0 + j;
     if (co >= cout) continue;
     for (int e = tx; e < row_elems; e += 32) {
       const int i = e / taps, tap = e - i * taps;
       const int ci = ci0 + i;
-      if (ci < cin_eff) out[(1LL * co * cin_eff + ci) * taps + tap] = tile[(tap * 32 + i) * 33 + j];
+      if (ci < cin_eff) out[(1LL * co * cin_eff + ci) * taps + tap] = tile[(tap * bci + i) * 33 + j];
     }
   }
 }
 
 struct WgradPlan {
   WgradParams p;
+  int BN;
   int grid;
   int smem;
   long long ws_bytes;
@@ -236,56 +286,56 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
               "conv_wgrad: channels must be padded to multiples of 64 (cin %d, cout %d)", x.c, dy.c);
   WgradParams& p = plan->p;
   memset(&p, 0, sizeof(p));
-  // K block = 64-pixel patch; pick the power-of-two shape that wastes the fewest rows on this image size
-  double best = -1.0;
-  for (int pn = 1; pn <= 64; pn *= 2)
-    for (int ph = 1; ph * pn <= 64; ph *= 2) {
-      int pw = 64 / (pn * ph);
-      if (pw > 256) continue;
-      long long tiles = 1LL * ((x.n + pn - 1) / pn) * ((x.h + ph - 1) / ph) * ((x.w + pw - 1) / pw);
-      double eff = static_cast<double>(1LL * x.n * x.h * x.w) / static_cast<double>(tiles * 64);
-      double score = eff - 1e-4 * (pn > 1) + 1e-6 * pw;
-      if (score > best) {
-        best = score;
-        p.PW = pw; p.PH = ph; p.PN = pn;
-      }
-    }
-  p.tiles_w = (x.w + p.PW - 1) / p.PW;
-  p.tiles_h = (x.h + p.PH - 1) / p.PH;
-  p.tiles_n = (x.n + p.PN - 1) / p.PN;
-  long long kt = 1LL * p.tiles_w * p.tiles_h * p.tiles_n;
-  CVB_REQUIRE(kt < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_wgrad: too many K blocks");
-  p.kt_total = static_cast<int>(kt);
+  p.N = x.n; p.H = x.h; p.W = x.w;
+  p.tiles_w = (x.w + kWTileW - 1) / kWTileW;
+  p.tiles_h = (x.h + kWTileH - 1) / kWTileH;
+  long long tiles = 1LL * p.tiles_w * p.tiles_h * x.n;
+  CVB_REQUIRE(tiles < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_wgrad: too many pixel tiles");
+  p.total_tiles = static_cast<int>(tiles);
   p.taps = taps;
   p.cin_pad = x.c;
   p.cout_pad = dy.c;
-  p.BN = (dy.c % 256 == 0) ? 256 : ((dy.c % 128 == 0) ? 128 : 64);
+  const int BN = (dy.c % 256 == 0) ? 256 : ((dy.c % 128 == 0) ? 128 : 64);
+  plan->BN = BN;
   p.CM = (x.c % 128 == 0) ? 2 : 1;
-  const int max_accs = 512 / p.BN;
-  const int max_units = p.BN == 256 ? 4 : 6;  // keeps a stage <= 64 KB so three stages fit
-  int T = (max_units / p.CM);
-  if (T > 2 * max_accs / p.CM) T = 2 * max_accs / p.CM;
-  if (T > taps) T = taps;
-  if (T < 1) T = 1;
-  p.T = T;
-  p.n_co_tiles = dy.c / p.BN;
+  // accumulators: accs * BN <= 512 TMEM columns, accs <= kMaxAccs; one accumulator = two 64-row atoms
+  int max_accs = 512 / BN;
+  if (max_accs > kMaxAccs) max_accs = kMaxAccs;
+  const int max_taps = p.CM == 2 ? max_accs : 2 * max_accs;  // taps per item
+  p.n_tap_groups = (taps + max_taps - 1) / max_taps;
+  p.T = (taps + p.n_tap_groups - 1) / p.n_tap_groups;  // balanced groups
+  p.n_tap_groups = (taps + p.T - 1) / p.T;
+  p.n_co_tiles = dy.c / BN;
   p.n_ci_tiles = x.c / (64 * p.CM);
-  p.n_tap_groups = (taps + T - 1) / T;
-  p.units_pad = ((T * p.CM + 1) / 2) * 2;
-  const int stage_bytes = (p.units_pad + p.BN / 64) * kUnitBytes;
-  p.stages = kWgradSmemBudget / stage_bytes;
-  if (p.stages > 8) p.stages = 8;
-  CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", stage_bytes);
+  p.stage_bytes = p.CM * kWPatchStride + (BN / 64) * kWDyBytes;
+  p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
   const int items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
-  int splits = (2 * sm_count() + items - 1) / items;
-  int max_splits = p.kt_total / 8;
+  // K splits: about two CTAs per SM in total (one resident at a time), never fewer than 4 pixel tiles per CTA
+  const int target = 2 * sm_count();
+  int splits = (target + items / 2) / items;
+  int max_splits = p.total_tiles / 4;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.splits = splits;
   plan->grid = items * splits;
-  plan->smem = 1024 + p.stages * stage_bytes + 256;
+  plan->smem = 1024 + p.stages * p.stage_bytes + 256;
   plan->ws_bytes = 1LL * splits * taps * x.c * dy.c * 4;
+  return CVB_OK;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kWgradSmemBudget));
+    configured = true;
+  }
+  conv_wgrad_kernel<BN><<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
+  CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
 
@@ -318,22 +368,23 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, CVB_ERR_INVALID_ARG, "conv_wgrad: workspace not 16-byte aligned");
   plan.p.ws = static_cast<float*>(workspace);
   CUtensorMap tmX, tmDY;
-  rc = make_act_tmap(&tmX, x, plan.p.PW, plan.p.PH, plan.p.PN);
+  rc = make_act_tmap(&tmX, x, kWTileW + 2, kWTileH + 2, 1);
   if (rc) return rc;
-  rc = make_act_tmap(&tmDY, dy, plan.p.PW, plan.p.PH, plan.p.PN);
+  rc = make_act_tmap(&tmDY, dy, kWTileW, kWTileH, 1);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  1024 + kWgradSmemBudget + 256));
-    configured = true;
-  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  conv_wgrad_kernel<<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
-  CVB_LAUNCH_CHECK();
-  dim3 rgrid((dy.c + 31) / 32, (x.c + 31) / 32);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * 32 * 33 * sizeof(float), st>>>(plan.p.ws, plan.p.splits, taps, x.c, dy.c,
-                                                                         cout, cin_eff, dw);
+  switch (plan.BN) {
+    case 256: rc = launch_wgrad<256>(tmX, tmDY, plan, st); break;
+    case 128: rc = launch_wgrad<128>(tmX, tmDY, plan, st); break;
+    default: rc = launch_wgrad<64>(tmX, tmDY, plan, st); break;
+  }
+  if (rc) return rc;
+  // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
+  int bci = 32;
+  while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((x.c + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
+  dim3 rgrid((dy.c + 31) / 32, (x.c + bci - 1) / bci);
+  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, plan.p.splits, taps, x.c, dy.c,
+                                                                          cout, cin_eff, bci, dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
