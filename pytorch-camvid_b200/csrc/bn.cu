@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, co
   const int ppb = kThreads / CV;  // pixels handled per block iteration (CV divides kThreads, checked on host)
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
-  const long long npix = 1LL * y.n * y.h * y.w;
+  const unsigned npix = static_cast<unsigned>(y.n) * y.h * y.w;
 
   float s1[8], s2[8], sc[8], sh[8];
 #pragma unroll
@@ -30,27 +30,37 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, co
     ld8f(scale + cv * 8, sc);
     ld8f(shift + cv * 8, sh);
   }
-  for (long long pix = 1LL * blockIdx.x * ppb + pl; pix < npix; pix += 1LL * gridDim.x * ppb) {
-    int w = static_cast<int>(pix % y.w);
-    long long t = pix / y.w;
-    int h = static_cast<int>(t % y.h);
-    int n = static_cast<int>(t / y.h);
-    float fy[8];
-    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), fy);
-    if (MODE == 0) {
+  const unsigned step = gridDim.x * ppb;
+  for (unsigned pix = blockIdx.x * ppb + pl; pix < npix; pix += 2 * step) {
+    const unsigned pix2 = pix + step;
+    const bool has2 = pix2 < npix;
+    // all loads of both pixels are issued before the arithmetic
+    const uint4 uy = ldg16(y.p + poff(y, pix) + cv * 8);
+    uint4 uy2 = make_uint4(0, 0, 0, 0), ud = uy2, ud2 = uy2;
+    if (has2) uy2 = ldg16(y.p + poff(y, pix2) + cv * 8);
+    if (MODE == 1) {
+      ud = ldg16(da.p + poff(da, pix) + cv * 8);
+      if (has2) ud2 = ldg16(da.p + poff(da, pix2) + cv * 8);
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += fy[j];
-        s2[j] = fmaf(fy[j], fy[j], s2[j]);
-      }
-    } else {
-      float fd[8];
-      unpack8(ldg16(da.p + voff(da, n, h, w) + cv * 8), fd);
+    for (int rep = 0; rep < 2; ++rep) {
+      if (rep == 1 && !has2) break;
+      float fy[8], fd[8];
+      unpack8(rep == 0 ? uy : uy2, fy);
+      if (MODE == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
-        s1[j] += g;
-        s2[j] = fmaf(g, fy[j], s2[j]);
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += fy[j];
+          s2[j] = fmaf(fy[j], fy[j], s2[j]);
+        }
+      } else {
+        unpack8(rep == 0 ? ud : ud2, fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+          s1[j] += g;
+          s2[j] = fmaf(g, fy[j], s2[j]);
+        }
       }
     }
   }
@@ -78,6 +88,7 @@ static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
   CVB_REQUIRE(CV <= kThreads && (kThreads % CV) == 0, CVB_ERR_UNSUPPORTED,
               "bn reduce: channels %d must divide %d", v.c, kThreads * 8);
   CVB_REQUIRE(rows > 0, CVB_ERR_INVALID_ARG, "bn reduce: rows must be positive");
+  CVB_REQUIRE(fits_u32(v), CVB_ERR_UNSUPPORTED, "bn reduce: view too large for 32-bit indexing");
   *grid = rows;
   return CVB_OK;
 }
@@ -186,52 +197,75 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(View y, View a, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift) {
-  const int CV = y.c >> 3;
-  const long long total = 1LL * y.n * y.h * y.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    long long pix = i / CV;
-    int w = static_cast<int>(pix % y.w);
-    long long t = pix / y.w;
-    int h = static_cast<int>(t % y.h);
-    int n = static_cast<int>(t / y.h);
+  const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
+  const unsigned stride = gridDim.x * kThreads;
+  // two independent elements per iteration (both loads issued before either store)
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += 2 * stride) {
+    const unsigned i2 = i + stride;
+    const bool has2 = i2 < total;
+    unsigned pix, cv, pix2 = 0, cv2 = 0;
+    split_cv(y, i, pix, cv);
+    if (has2) split_cv(y, i2, pix2, cv2);
+    uint4 u = ldg16(y.p + poff(y, pix) + cv * 8), u2 = make_uint4(0, 0, 0, 0);
+    if (has2) u2 = ldg16(y.p + poff(y, pix2) + cv2 * 8);
     float f[8], sc[8], sh[8];
-    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), f);
+    unpack8(u, f);
     ld8f(scale + cv * 8, sc);
     ld8f(shift + cv * 8, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-    stg16(a.p + voff(a, n, h, w) + cv * 8, pack8(f));
+    stg16(a.p + poff(a, pix) + cv * 8, pack8(f));
+    if (has2) {
+      unpack8(u2, f);
+      ld8f(scale + cv2 * 8, sc);
+      ld8f(shift + cv2 * 8, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+      stg16(a.p + poff(a, pix2) + cv2 * 8, pack8(f));
+    }
   }
+}
+
+__device__ __forceinline__ uint4 bn_bwd_elem(const uint4& uy, const uint4& ud, const float* __restrict__ scale,
+                                             const float* __restrict__ shift, const float* __restrict__ coef,
+                                             int c_pad, unsigned cv) {
+  float fy[8], fd[8], sc[8], sh[8], c0[8], c1[8], c2[8], o[8];
+  unpack8(uy, fy);
+  unpack8(ud, fd);
+  ld8f(scale + cv * 8, sc);
+  ld8f(shift + cv * 8, sh);
+  ld8f(coef + cv * 8, c0);
+  ld8f(coef + c_pad + cv * 8, c1);
+  ld8f(coef + 2 * c_pad + cv * 8, c2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+    o[j] = fmaf(g, c0[j], fmaf(fy[j], c1[j], c2[j]));
+  }
+  return pack8(o);
 }
 
 __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, View y, View dy,
                                                                       const float* __restrict__ scale,
                                                                       const float* __restrict__ shift,
                                                                       const float* __restrict__ coef, int c_pad) {
-  const int CV = y.c >> 3;
-  const long long total = 1LL * y.n * y.h * y.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    long long pix = i / CV;
-    int w = static_cast<int>(pix % y.w);
-    long long t = pix / y.w;
-    int h = static_cast<int>(t % y.h);
-    int n = static_cast<int>(t / y.h);
-    float fy[8], fd[8], sc[8], sh[8], c0[8], c1[8], c2[8], o[8];
-    unpack8(ldg16(y.p + voff(y, n, h, w) + cv * 8), fy);
-    unpack8(ldg16(da.p + voff(da, n, h, w) + cv * 8), fd);
-    ld8f(scale + cv * 8, sc);
-    ld8f(shift + cv * 8, sh);
-    ld8f(coef + cv * 8, c0);
-    ld8f(coef + c_pad + cv * 8, c1);
-    ld8f(coef + 2 * c_pad + cv * 8, c2);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
-      o[j] = fmaf(g, c0[j], fmaf(fy[j], c1[j], c2[j]));
+  const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
+  const unsigned stride = gridDim.x * kThreads;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += 2 * stride) {
+    const unsigned i2 = i + stride;
+    const bool has2 = i2 < total;
+    unsigned pix, cv, pix2 = 0, cv2 = 0;
+    split_cv(y, i, pix, cv);
+    if (has2) split_cv(y, i2, pix2, cv2);
+    const uint4 uy = ldg16(y.p + poff(y, pix) + cv * 8);
+    const uint4 ud = ldg16(da.p + poff(da, pix) + cv * 8);
+    uint4 uy2 = make_uint4(0, 0, 0, 0), ud2 = uy2;
+    if (has2) {
+      uy2 = ldg16(y.p + poff(y, pix2) + cv2 * 8);
+      ud2 = ldg16(da.p + poff(da, pix2) + cv2 * 8);
     }
-    stg16(dy.p + voff(dy, n, h, w) + cv * 8, pack8(o));
+    stg16(dy.p + poff(dy, pix) + cv * 8, bn_bwd_elem(uy, ud, scale, shift, coef, c_pad, cv));
+    if (has2) stg16(dy.p + poff(dy, pix2) + cv2 * 8, bn_bwd_elem(uy2, ud2, scale, shift, coef, c_pad, cv2));
   }
 }
 
@@ -306,9 +340,10 @@ extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* sh
   rc = check_view(a, "bn_relu_apply.a");
   if (rc) return rc;
   CVB_REQUIRE(same_shape(y, a), CVB_ERR_INVALID_ARG, "bn_relu_apply: shapes differ");
+  CVB_REQUIRE(fits_u32(y), CVB_ERR_UNSUPPORTED, "bn_relu_apply: view too large for 32-bit indexing");
   CVB_REQUIRE(scale && shift, CVB_ERR_INVALID_ARG, "bn_relu_apply: null scale/shift");
   long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
-  bn_relu_apply_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_relu_apply_kernel<<<ew_grid((total + 1) / 2, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       to_dev(y), to_dev(a), scale, shift);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
@@ -323,9 +358,10 @@ extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale
   rc = check_view(dy, "bn_bwd_apply.dy");
   if (rc) return rc;
   CVB_REQUIRE(same_shape(y, da) && same_shape(y, dy), CVB_ERR_INVALID_ARG, "bn_bwd_apply: shapes differ");
+  CVB_REQUIRE(fits_u32(y), CVB_ERR_UNSUPPORTED, "bn_bwd_apply: view too large for 32-bit indexing");
   CVB_REQUIRE(scale && shift && coef, CVB_ERR_INVALID_ARG, "bn_bwd_apply: null pointer");
   long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
-  bn_relu_bwd_apply_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_relu_bwd_apply_kernel<<<ew_grid((total + 1) / 2, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

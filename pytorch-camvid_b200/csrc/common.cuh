@@ -68,16 +68,45 @@ struct View {  // device copy of cvb_view with typed pointer
   __nv_bfloat16* p;
   int n, h, w, c;
   long long sn, sh, sw;
+  int dense;     // pixels are equally spaced: offset(pixel index) = index * sw (true for whole buffers and channel slices)
+  int cv_shift;  // log2(c / 8) when c / 8 is a power of two, else -1
 };
 inline View to_dev(const cvb_view& v) {
   View d;
   d.p = static_cast<__nv_bfloat16*>(v.ptr);
   d.n = v.n; d.h = v.h; d.w = v.w; d.c = v.c;
   d.sn = v.sn; d.sh = v.sh; d.sw = v.sw;
+  d.dense = (v.sh == v.w * v.sw && v.sn == v.h * v.sh) ? 1 : 0;
+  const int cv = v.c / 8;
+  d.cv_shift = -1;
+  for (int s = 0; s < 12; ++s)
+    if ((1 << s) == cv) d.cv_shift = s;
   return d;
 }
+// Elementwise kernels index (pixel, 8-channel vector) pairs with 32-bit arithmetic; hosts check this bound.
+inline bool fits_u32(const cvb_view& v) { return 1LL * v.n * v.h * v.w * (v.c / 8) < (1LL << 31); }
 
 __device__ __forceinline__ long long voff(const View& v, int n, int h, int w) {
+  return n * v.sn + h * v.sh + w * v.sw;
+}
+// element index -> (pixel, channel vector) without 64-bit division
+__device__ __forceinline__ void split_cv(const View& v, unsigned i, unsigned& pix, unsigned& cv) {
+  if (v.cv_shift >= 0) {
+    pix = i >> v.cv_shift;
+    cv = i & ((1u << v.cv_shift) - 1u);
+  } else {
+    const unsigned CV = static_cast<unsigned>(v.c) >> 3;
+    pix = i / CV;
+    cv = i - pix * CV;
+  }
+}
+// offset of a linear pixel index (n, h, w flattened over the view's own extents)
+__device__ __forceinline__ long long poff(const View& v, unsigned pix) {
+  if (v.dense) return static_cast<long long>(pix) * v.sw;
+  const unsigned w = pix % static_cast<unsigned>(v.w);
+  const unsigned t = pix / static_cast<unsigned>(v.w);
+  const unsigned h = t % static_cast<unsigned>(v.h);
+  const unsigned n = t / static_cast<unsigned>(v.h);
   return n * v.sn + h * v.sh + w * v.sw;
 }
 

@@ -7,41 +7,42 @@ namespace cvb {
 
 constexpr int kThreads = 256;
 
-// thread = (pixel, 8-channel group); consecutive threads = consecutive pixels (coalesced plane reads)
+// thread = one pixel: its channels are gathered from the NCHW planes (consecutive threads read consecutive pixels of a
+// plane: coalesced) and the whole NHWC row of the pixel is written as consecutive 16-byte vectors, so a warp writes
+// 32 complete rows (no partially written 128-byte lines left for other blocks to finish).
 __global__ void __launch_bounds__(kThreads) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int c_src,
                                                                           View dst) {
   const int CV = dst.c >> 3;
-  const long long hw = 1LL * dst.h * dst.w;
-  const long long total = 1LL * dst.n * hw * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    long long p = i % hw;
-    long long t = i / hw;
-    int cv = static_cast<int>(t % CV);
-    int n = static_cast<int>(t / CV);
-    int h = static_cast<int>(p / dst.w), w = static_cast<int>(p % dst.w);
-    float f[8];
+  const unsigned hw = static_cast<unsigned>(dst.h) * dst.w;
+  const unsigned total = static_cast<unsigned>(dst.n) * hw;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned n = i / hw, p = i - n * hw;
+    const float* sp = src + static_cast<long long>(n) * c_src * hw + p;
+    __nv_bfloat16* dp = dst.p + poff(dst, i);
+    for (int cv = 0; cv < CV; ++cv) {
+      float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = cv * 8 + j;
-      f[j] = c < c_src ? __ldg(src + (1LL * n * c_src + c) * hw + p) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        f[j] = c < c_src ? __ldg(sp + static_cast<long long>(c) * hw) : 0.f;
+      }
+      stg16(dp + cv * 8, pack8(f));
     }
-    stg16(dst.p + voff(dst, n, h, w) + cv * 8, pack8(f));
   }
 }
 
 __global__ void __launch_bounds__(kThreads) nhwc_bf16_to_nchw_f32_kernel(View src, float* __restrict__ dst,
                                                                           int c_dst) {
   const int CV = (c_dst + 7) >> 3;
-  const long long hw = 1LL * src.h * src.w;
-  const long long total = 1LL * src.n * hw * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    long long p = i % hw;
-    long long t = i / hw;
-    int cv = static_cast<int>(t % CV);
-    int n = static_cast<int>(t / CV);
-    int h = static_cast<int>(p / src.w), w = static_cast<int>(p % src.w);
+  const unsigned hw = static_cast<unsigned>(src.h) * src.w;
+  const unsigned total = static_cast<unsigned>(src.n) * hw * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned p = i % hw;
+    const unsigned t = i / hw;
+    const int cv = static_cast<int>(t % CV);
+    const int n = static_cast<int>(t / CV);
     float f[8];
-    unpack8(ldg16(src.p + voff(src, n, h, w) + cv * 8), f);
+    unpack8(ldg16(src.p + poff(src, n * hw + p) + cv * 8), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int c = cv * 8 + j;
@@ -50,41 +51,43 @@ __global__ void __launch_bounds__(kThreads) nhwc_bf16_to_nchw_f32_kernel(View sr
   }
 }
 
-// dst channel k = ci*9 + r*3 + s  <-  x[n, ci, h+r-1, w+s-1]
+// dst channel k = ci*9 + r*3 + s  <-  x[n, ci, h+r-1, w+s-1]; thread = one pixel (see above)
 __global__ void __launch_bounds__(kThreads) im2col3x3_kernel(const float* __restrict__ src, int c_src, View dst) {
   const int CV = dst.c >> 3;
-  const long long hw = 1LL * dst.h * dst.w;
-  const long long total = 1LL * dst.n * hw * CV;
+  const unsigned hw = static_cast<unsigned>(dst.h) * dst.w;
+  const unsigned total = static_cast<unsigned>(dst.n) * hw;
   const int kmax = c_src * 9;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    long long p = i % hw;
-    long long t = i / hw;
-    int cv = static_cast<int>(t % CV);
-    int n = static_cast<int>(t / CV);
-    int h = static_cast<int>(p / dst.w), w = static_cast<int>(p % dst.w);
-    float f[8];
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned n = i / hw, p = i - n * hw;
+    const int h = static_cast<int>(p / dst.w), w = static_cast<int>(p - (p / dst.w) * dst.w);
+    const float* sp = src + static_cast<long long>(n) * c_src * hw;
+    __nv_bfloat16* dp = dst.p + poff(dst, i);
+    for (int cv = 0; cv < CV; ++cv) {
+      float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int k = cv * 8 + j;
-      float v = 0.f;
-      if (k < kmax) {
-        int ci = k / 9, tap = k % 9;
-        int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < dst.h && ww >= 0 && ww < dst.w) v = __ldg(src + (1LL * n * c_src + ci) * hw + 1LL * hh * dst.w + ww);
+      for (int j = 0; j < 8; ++j) {
+        const int k = cv * 8 + j;
+        float v = 0.f;
+        if (k < kmax) {
+          const int ci = k / 9, tap = k - ci * 9;
+          const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+          if (hh >= 0 && hh < dst.h && ww >= 0 && ww < dst.w)
+            v = __ldg(sp + static_cast<long long>(ci) * hw + static_cast<unsigned>(hh) * dst.w + ww);
+        }
+        f[j] = v;
       }
-      f[j] = v;
+      stg16(dp + cv * 8, pack8(f));
     }
-    stg16(dst.p + voff(dst, n, h, w) + cv * 8, pack8(f));
   }
 }
 
 // dst[co][tap][ci] (bf16) <- w[co][ci][tap] (fp32 OIHW); taps==1: dst[co][k] <- w[co][k], k < cin*9
 __global__ void pack_w_fprop_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad,
                                     int cin_pad, __nv_bfloat16* __restrict__ dst) {
-  const long long total = 1LL * cout_pad * taps * cin_pad;
-  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+  const unsigned total = 1u * cout_pad * taps * cin_pad;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int ci = static_cast<int>(i % cin_pad);
-    long long t = i / cin_pad;
+    unsigned t = i / cin_pad;
     int tap = static_cast<int>(t % taps);
     int co = static_cast<int>(t / taps);
     float v = 0.f;
@@ -102,10 +105,10 @@ __global__ void pack_w_fprop_kernel(const float* __restrict__ w, int cout, int c
 // dst[ci][tap'][co] (bf16) <- w[co][ci][8 - tap'] : the 180-degree rotated, in/out-transposed filter
 __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int cout_pad, int cin_pad,
                                     __nv_bfloat16* __restrict__ dst) {
-  const long long total = 1LL * cin_pad * 9 * cout_pad;
-  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+  const unsigned total = 1u * cin_pad * 9 * cout_pad;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int co = static_cast<int>(i % cout_pad);
-    long long t = i / cout_pad;
+    unsigned t = i / cout_pad;
     int tap = static_cast<int>(t % 9);
     int ci = static_cast<int>(t / 9);
     float v = 0.f;
@@ -116,15 +119,11 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int c
 
 __global__ void __launch_bounds__(kThreads) zero_view_kernel(View v) {
   const int CV = v.c >> 3;
-  const long long total = 1LL * v.n * v.h * v.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    long long pix = i / CV;
-    int w = static_cast<int>(pix % v.w);
-    long long t = pix / v.w;
-    int h = static_cast<int>(t % v.h);
-    int n = static_cast<int>(t / v.h);
-    stg16(v.p + voff(v, n, h, w) + cv * 8, make_uint4(0, 0, 0, 0));
+  const unsigned total = 1u * v.n * v.h * v.w * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    unsigned pix, cv;
+    split_cv(v, i, pix, cv);
+    stg16(v.p + poff(v, pix) + cv * 8, make_uint4(0, 0, 0, 0));
   }
 }
 
@@ -137,7 +136,7 @@ extern "C" int cvb_nchw_f32_to_nhwc_bf16(const float* src, int c_src, cvb_view d
   if (rc) return rc;
   CVB_REQUIRE(src && c_src > 0 && c_src <= dst.c, CVB_ERR_INVALID_ARG, "nchw_to_nhwc: bad source (c_src=%d, dst.c=%d)",
               c_src, dst.c);
-  long long total = 1LL * dst.n * dst.h * dst.w * (dst.c / 8);
+  long long total = 1LL * dst.n * dst.h * dst.w;
   nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       src, c_src, to_dev(dst));
   CVB_LAUNCH_CHECK();
@@ -161,7 +160,7 @@ extern "C" int cvb_im2col3x3_nchw_f32(const float* src, int c_src, cvb_view dst,
   if (rc) return rc;
   CVB_REQUIRE(src && c_src > 0 && c_src * 9 <= dst.c, CVB_ERR_INVALID_ARG,
               "im2col3x3: 9*c_src=%d does not fit the %d destination channels", c_src * 9, dst.c);
-  long long total = 1LL * dst.n * dst.h * dst.w * (dst.c / 8);
+  long long total = 1LL * dst.n * dst.h * dst.w;
   im2col3x3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, c_src,
                                                                                                   to_dev(dst));
   CVB_LAUNCH_CHECK();

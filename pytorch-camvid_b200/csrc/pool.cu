@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(View x, View a, V
                                                                 uint8_t* __restrict__ code) {
   const int CV = x.c >> 3;
   const int HO = (x.h + 1) >> 1, WO = (x.w + 1) >> 1;
-  const long long total = 1LL * x.n * HO * WO * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+  const unsigned total = 1u * x.n * HO * WO * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     int cv = static_cast<int>(i % CV);
-    long long t = i / CV;
+    unsigned t = i / CV;
     int wo = static_cast<int>(t % WO);
     t /= WO;
     int ho = static_cast<int>(t % HO);
@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(kThreads) pool_scatter_kernel(View dout, View 
                                                                  const uint8_t* __restrict__ code) {
   const int CV = dx.c >> 3;
   const int HO = (dx.h + 1) >> 1, WO = (dx.w + 1) >> 1;
-  const long long total = 1LL * dx.n * HO * WO * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+  const unsigned total = 1u * dx.n * HO * WO * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     int cv = static_cast<int>(i % CV);
-    long long t = i / CV;
+    unsigned t = i / CV;
     int wo = static_cast<int>(t % WO);
     t /= WO;
     int ho = static_cast<int>(t % HO);
@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(kThreads) pool_scatter_kernel(View dout, View 
 // dx[n,ho,wo,c] = dout[n, 2ho+dh, 2wo+dw, c] with (dh,dw) from the code  (MaxUnpool backward)
 __global__ void __launch_bounds__(kThreads) pool_gather_kernel(View dout, View dx, const uint8_t* __restrict__ code) {
   const int CV = dx.c >> 3;
-  const long long total = 1LL * dx.n * dx.h * dx.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
+  const unsigned total = 1u * dx.n * dx.h * dx.w * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     int cv = static_cast<int>(i % CV);
-    long long t = i / CV;
+    unsigned t = i / CV;
     int wo = static_cast<int>(t % dx.w);
     t /= dx.w;
     int ho = static_cast<int>(t % dx.h);
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(kThreads) pool_gather_kernel(View dout, View d
 
 __global__ void pool_code_to_index_kernel(const uint8_t* __restrict__ code, int n, int ho, int wo, int c, int w_in,
                                           int64_t* __restrict__ idx) {
-  const long long total = 1LL * n * c * ho * wo;
-  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+  const unsigned total = 1u * n * c * ho * wo;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int x = static_cast<int>(i % wo);
-    long long t = i / wo;
+    unsigned t = i / wo;
     int y = static_cast<int>(t % ho);
     t /= ho;
     int ch = static_cast<int>(t % c);

@@ -18,10 +18,10 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
 
 __global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View out, float sy, float sx) {
   const int CV = x.c >> 3;
-  const long long total = 1LL * out.n * out.h * out.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    long long t = i / CV;
+  const unsigned total = 1u * out.n * out.h * out.w * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    unsigned t, cv;
+    split_cv(out, i, t, cv);
     int ox = static_cast<int>(t % out.w);
     t /= out.w;
     int oy = static_cast<int>(t % out.h);
@@ -49,34 +49,52 @@ __device__ __forceinline__ float tap_weight(float scale, int dst, int in, int ta
   return (i0 == target ? l0 : 0.f) + (i1 == target ? l1 : 0.f);
 }
 
+// Output positions whose stencil touches input position `target`, with their weights (at most 6 for a x2 upsample:
+// sources lie in the open interval (target-1, target+1), 2/scale wide).
+__device__ __forceinline__ int gather_taps(float scale, float inv, int in, int out, int target, int (&idx)[6],
+                                           float (&wgt)[6]) {
+  const int lo = max(0, static_cast<int>(floorf((target - 1) * inv)) - 1);
+  const int hi = min(out - 1, static_cast<int>(ceilf((target + 1) * inv)) + 1);
+  int cnt = 0;
+  for (int o = lo; o <= hi; ++o) {
+    const float w = tap_weight(scale, o, in, target);
+    if (w != 0.f && cnt < 6) {
+      idx[cnt] = o;
+      wgt[cnt] = w;
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
 __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, View dx, float sy, float sx, float isy,
                                                                    float isx) {
   const int CV = dx.c >> 3;
-  const long long total = 1LL * dx.n * dx.h * dx.w * CV;
-  for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < total; i += 1LL * gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    long long t = i / CV;
-    int ix = static_cast<int>(t % dx.w);
-    t /= dx.w;
-    int iy = static_cast<int>(t % dx.h);
-    int n = static_cast<int>(t / dx.h);
-    // outputs with src in (iy-1, iy+1): generous integer bounds, exact membership via tap_weight
-    int oy_lo = max(0, static_cast<int>(floorf((iy - 1) * isy)) - 1);
-    int oy_hi = min(dout.h - 1, static_cast<int>(ceilf((iy + 1) * isy)) + 1);
-    int ox_lo = max(0, static_cast<int>(floorf((ix - 1) * isx)) - 1);
-    int ox_hi = min(dout.w - 1, static_cast<int>(ceilf((ix + 1) * isx)) + 1);
+  const unsigned total = 1u * dx.n * dx.h * dx.w * CV;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    unsigned pix, cv;
+    split_cv(dx, i, pix, cv);
+    const int ix = static_cast<int>(pix % dx.w);
+    const unsigned t = pix / dx.w;
+    const int iy = static_cast<int>(t % dx.h);
+    const int n = static_cast<int>(t / dx.h);
+    int oy[6], ox[6];
+    float wy[6], wx[6];
+    const int ny = gather_taps(sy, isy, dx.h, dout.h, iy, oy, wy);
+    const int nx = gather_taps(sx, isx, dx.w, dout.w, ix, ox, wx);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      float wy = tap_weight(sy, oy, dx.h, iy);
-      if (wy == 0.f) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        float wx = tap_weight(sx, ox, dx.w, ix);
-        if (wx == 0.f) continue;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      if (a >= ny) break;
+      const __nv_bfloat16* rowp = dout.p + n * dout.sn + oy[a] * dout.sh + cv * 8;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        if (b >= nx) break;
         float g[8];
-        unpack8(ldg16(dout.p + voff(dout, n, oy, ox) + cv * 8), g);
-        float wgt = wy * wx;
+        unpack8(ldg16(rowp + ox[b] * dout.sw), g);
+        const float wgt = wy[a] * wx[b];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, g[j], acc[j]);
       }
