@@ -128,6 +128,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+// streaming variants for single-use data (evict-first: keep L2 for the tensors the next kernel re-reads)
+__device__ __forceinline__ uint4 ldg16_cs(const __nv_bfloat16* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
   float4 a = __ldg(reinterpret_cast<const float4*>(p));
   float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);

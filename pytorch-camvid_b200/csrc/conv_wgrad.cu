@@ -14,9 +14,12 @@
 //     tools/exp/exp_desc.cu). The dy tile is fetched once and shared by all taps.
 //   * M = 128 = two 64-row atoms: two input-channel chunks of one tap (cin >= 128; LBO = chunk stride in smem) or two
 //     taps of a 64-channel input (LBO = distance between the two tap views).
-//   * a CTA owns one work item = (co tile, ci tile, tap group, K split) and keeps one fp32 accumulator per atom pair
-//     in TMEM for its whole pixel range; split-K partials go to a workspace that a second kernel reduces and transposes
-//     to the OIHW fp32 layout of nn.Conv2d.weight.grad (deterministic, no atomics).
+//   * work item = (co tile, ci tile, tap group): one fp32 accumulator per atom pair in TMEM, up to 512 columns.
+//   * stream-K partition: the (item, pixel tile) space is flattened and cut into one EQUAL contiguous range per CTA
+//     (grid = number of SMs, a single balanced wave whatever the item count). A CTA that crosses an item boundary
+//     drains its accumulators to the workspace (one "part" of that item) and carries on with the next item. Parts are
+//     summed and transposed to the OIHW fp32 layout of nn.Conv2d.weight.grad by two small kernels (deterministic, no
+//     atomics).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tma_host.h"
@@ -39,10 +42,22 @@ struct WgradParams {
   int taps;  // 9 or 1
   int cin_pad, cout_pad;
   int CM, T;  // 64-channel ci chunks per M=128 accumulator (1 or 2), taps per work item
-  int n_co_tiles, n_ci_tiles, n_tap_groups, splits;
+  int n_co_tiles, n_ci_tiles, n_tap_groups, items;
+  int grid;               // CTAs = ranges of the flattened (item, tile) space
+  long long total_units;  // items * total_tiles
+  int slots;              // workspace parts per item
   int stages, stage_bytes;
-  float* ws;  // [splits][taps][cin_pad][cout_pad]
+  float* ws;  // [slots][taps][cin_pad][cout_pad]; part k of an item lives in slot k (k < parts of that item)
 };
+
+// Stream-K bookkeeping shared by host and device: CTA c owns units [c*U/G, (c+1)*U/G).
+__host__ __device__ inline long long sk_begin(long long U, int G, int c) { return U * c / G; }
+__host__ __device__ inline int sk_owner(long long U, int G, long long u) {  // the CTA whose range contains unit u
+  int c = static_cast<int>(u * G / U);
+  while (c + 1 < G && sk_begin(U, G, c + 1) <= u) ++c;
+  while (c > 0 && sk_begin(U, G, c) > u) --c;
+  return c;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -54,25 +69,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work item decode
-  int item = blockIdx.x;
-  const int co_tile = item % p.n_co_tiles;
-  item /= p.n_co_tiles;
-  const int ci_tile = item % p.n_ci_tiles;
-  item /= p.n_ci_tiles;
-  const int tg = item % p.n_tap_groups;
-  const int split = item / p.n_tap_groups;
-  const int t0 = tg * p.T;
-  const int tcount = min(p.T, p.taps - t0);
-  const int units = tcount * p.CM;  // 64-row atoms this item accumulates
-  const int accs = (units + 1) >> 1;
-  const int tile_begin = static_cast<int>(1LL * p.total_tiles * split / p.splits);
-  const int tile_end = static_cast<int>(1LL * p.total_tiles * (split + 1) / p.splits);
+  const long long u_begin = sk_begin(p.total_units, p.grid, blockIdx.x);
+  const long long u_end = sk_begin(p.total_units, p.grid, blockIdx.x + 1);
+  const int item_first = static_cast<int>(u_begin / p.total_tiles);
+  const int item_last = u_end > u_begin ? static_cast<int>((u_end - 1) / p.total_tiles) : item_first - 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -84,6 +90,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&empty[i], 1);
     }
     mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -101,24 +108,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.CM) * kWPatchBytes + b_units * kWDyBytes;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int t = tile;
-        const int w0 = (t % p.tiles_w) * kWTileW;
-        t /= p.tiles_w;
-        const int h0 = (t % p.tiles_h) * kWTileH;
-        const int n0 = t / p.tiles_h;
-        uint8_t* sX = smem + stage * p.stage_bytes;
-        uint8_t* sD = sX + p.CM * kWPatchStride;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx_bytes);
-        for (int c = 0; c < p.CM; ++c)
-          tma_load_4d(sX + c * kWPatchStride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
+      for (int item = item_first; item <= item_last; ++item) {
+        const int co_tile = item % p.n_co_tiles;
+        const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
+        const long long base = 1LL * item * p.total_tiles;
+        const int tile_begin = static_cast<int>(max(u_begin, base) - base);
+        const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          int t = tile;
+          const int w0 = (t % p.tiles_w) * kWTileW;
+          t /= p.tiles_w;
+          const int h0 = (t % p.tiles_h) * kWTileH;
+          const int n0 = t / p.tiles_h;
+          uint8_t* sX = smem + stage * p.stage_bytes;
+          uint8_t* sD = sX + p.CM * kWPatchStride;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], tx_bytes);
+          for (int c = 0; c < p.CM; ++c)
+            tma_load_4d(sX + c * kWPatchStride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
 #pragma unroll
-        for (int j = 0; j < b_units; ++j)
-          tma_load_4d(sD + j * kWDyBytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+          for (int j = 0; j < b_units; ++j)
+            tma_load_4d(sD + j * kWDyBytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -127,97 +141,110 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     constexpr uint32_t idesc = idesc_bf16_f32(128, BN, true, true);
     constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive tile rows of the patch
     constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy tile rows are dense
-    // per accumulator: descriptor low word of its first atom relative to the stage base (row offset of the tap view,
-    // in 16-byte units) with the LBO field = distance to the second atom
-    uint32_t acc_lo[kMaxAccs];
-#pragma unroll
-    for (int j = 0; j < kMaxAccs; ++j) {
-      int tap_a, tap_b;
-      uint32_t lbo;
-      if (p.CM == 2) {
-        tap_a = tap_b = t0 + j;
-        lbo = kWPatchStride;
-      } else {
-        tap_a = t0 + 2 * j;
-        tap_b = tap_a + 1;
-        lbo = 0;
-      }
-      const int ra = p.taps == 9 ? (tap_a / 3) * kWPitch + tap_a % 3 : kWPitch + 1;
-      const int rb = p.taps == 9 ? (tap_b / 3) * kWPitch + tap_b % 3 : kWPitch + 2;
-      if (p.CM != 2) lbo = static_cast<uint32_t>(rb - ra) * 128;  // second atom = the next tap's view (positive)
-      acc_lo[j] = static_cast<uint32_t>(ra) * 8 + ((lbo >> 4) << 16);
-    }
     const uint32_t x_lo0 = desc_lo(smem_u32(smem), 0);
     const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * kWPatchStride, kWDyBytes);
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kWTileH;
-      const int rows = min(kWTileH, p.H - h0);
-      const int slices = (rows + 1) >> 1;  // K slices of two tile rows that touch the image
-      mbar_wait(&full[stage], phase);
-      tc_fence_after();
-      const uint32_t x_lo = x_lo0 + stage * stage_lo, d_lo = d_lo0 + stage * stage_lo;
-      const uint32_t first = tile != tile_begin ? 1u : 0u;
-      if (elect_one()) {
-        for (int s = 0; s < slices; ++s) {
-          const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
-          const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
+    int seg = 0;
+    for (int item = item_first; item <= item_last; ++item, ++seg) {
+      const int tg = item / (p.n_co_tiles * p.n_ci_tiles);
+      const int t0 = tg * p.T;
+      const int tcount = min(p.T, p.taps - t0);
+      const int accs = (tcount * p.CM + 1) >> 1;
+      // per accumulator: descriptor low word of its first atom relative to the stage base (row offset of the tap
+      // view, in 16-byte units) with the LBO field = distance to the second atom
+      uint32_t acc_lo[kMaxAccs];
 #pragma unroll
-          for (int j = 0; j < kMaxAccs; ++j)
-            if (j < accs) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+      for (int j = 0; j < kMaxAccs; ++j) {
+        const int tap_a = p.CM == 2 ? t0 + j : t0 + 2 * j;
+        const int tap_b = p.CM == 2 ? tap_a : tap_a + 1;
+        const int ra = p.taps == 9 ? (tap_a / 3) * kWPitch + tap_a % 3 : kWPitch + 1;
+        const int rb = p.taps == 9 ? (tap_b / 3) * kWPitch + tap_b % 3 : kWPitch + 2;
+        // second atom: the other ci chunk of the same tap (CM == 2) or the next tap's view of the same chunk
+        const uint32_t lbo = p.CM == 2 ? kWPatchStride : static_cast<uint32_t>(rb - ra) * 128;
+        acc_lo[j] = static_cast<uint32_t>(ra) * 8 + ((lbo >> 4) << 16);
+      }
+      const long long base = 1LL * item * p.total_tiles;
+      const int tile_begin = static_cast<int>(max(u_begin, base) - base);
+      const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
+      // the epilogue must have drained the previous item's accumulators
+      mbar_wait(tempty, (seg & 1) ^ 1);
+      tc_fence_after();
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kWTileH;
+        const int rows = min(kWTileH, p.H - h0);
+        const int slices = (rows + 1) >> 1;  // K slices of two tile rows that touch the image
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_lo = x_lo0 + stage * stage_lo, d_lo = d_lo0 + stage * stage_lo;
+        const uint32_t first = tile != tile_begin ? 1u : 0u;
+        if (elect_one()) {
+          for (int s = 0; s < slices; ++s) {
+            const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
+            const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < kMaxAccs; ++j)
+              if (j < accs) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+          }
+          umma_commit(&empty[stage]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(tfull);
       __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
-    if (elect_one()) umma_commit(tfull);
-    __syncwarp();
   } else if (warp >= 4) {
-    // --------------------------------- epilogue (once per CTA) -----------------------------------
+    // --------------------------------- epilogue (once per item segment) -----------------------------------
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
     const int atom = row >> 6, r = row & 63;
-    const bool has_work = tile_end > tile_begin;
-    if (has_work) {
-      mbar_wait(tfull, 0);
+    int seg = 0;
+    for (int item = item_first; item <= item_last; ++item, ++seg) {
+      const int co_tile = item % p.n_co_tiles;
+      const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
+      const int tg = item / (p.n_co_tiles * p.n_ci_tiles);
+      const int t0 = tg * p.T;
+      const int tcount = min(p.T, p.taps - t0);
+      const int units = tcount * p.CM;
+      const int accs = (units + 1) >> 1;
+      // this CTA's part number within the item = distance from the CTA that owns the item's first unit
+      const int part = static_cast<int>(blockIdx.x) - sk_owner(p.total_units, p.grid, 1LL * item * p.total_tiles);
+      mbar_wait(tfull, seg & 1);
       tc_fence_after();
-    }
-    for (int j = 0; j < accs; ++j) {
-      int tap, ci;
-      bool valid;
-      if (p.CM == 2) {
-        tap = t0 + j;
-        ci = (ci_tile * 2 + atom) * 64 + r;
-        valid = true;
-      } else {
-        const int u = 2 * j + atom;
-        valid = u < units;
-        tap = t0 + u;
-        ci = ci_tile * 64 + r;
-      }
-      float* dst = p.ws + ((static_cast<long long>(split) * p.taps + tap) * p.cin_pad + ci) * p.cout_pad + co_tile * BN;
+      for (int j = 0; j < accs; ++j) {
+        int tap, ci;
+        bool valid;
+        if (p.CM == 2) {
+          tap = t0 + j;
+          ci = (ci_tile * 2 + atom) * 64 + r;
+          valid = true;
+        } else {
+          const int u = 2 * j + atom;
+          valid = u < units;
+          tap = t0 + u;
+          ci = ci_tile * 64 + r;
+        }
+        float* dst = p.ws + ((static_cast<long long>(part) * p.taps + tap) * p.cin_pad + ci) * p.cout_pad + co_tile * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        if (has_work) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + j * BN + c0, v);
           tmem_ld_wait();
-        } else {
+          if (valid) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = 0;
-        }
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(dst + c0 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(dst + c0 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
     }
   }
   __syncwarp();
@@ -226,6 +253,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Part reduction, phase 1: slot 0 += slots 1 .. parts-1 of the item an element belongs to (16-byte accesses; the item and
+// its part count follow from the element's position with the same integer arithmetic the main kernel uses).
+__global__ void __launch_bounds__(256) wgrad_partsum_kernel(float* __restrict__ ws, WgradParams p, int BN) {
+  const long long n4 = 1LL * p.taps * p.cin_pad * p.cout_pad / 4;
+  float4* base = reinterpret_cast<float4*>(ws);
+  const int co4 = p.cout_pad / 4;
+  for (long long i = 1LL * blockIdx.x * 256 + threadIdx.x; i < n4; i += 1LL * gridDim.x * 256) {
+    const int co = static_cast<int>(i % co4) * 4;
+    const long long t = i / co4;
+    const int ci = static_cast<int>(t % p.cin_pad);
+    const int tap = static_cast<int>(t / p.cin_pad);
+    const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co / BN;
+    const long long u0 = 1LL * item * p.total_tiles;
+    const int parts = sk_owner(p.total_units, p.grid, u0 + p.total_tiles - 1) - sk_owner(p.total_units, p.grid, u0) + 1;
+    float4 acc = base[i];
+    for (int s = 1; s < parts; ++s) {
+      const float4 v = __ldcs(base + s * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    base[i] = acc;
   }
 }
 
@@ -311,18 +361,20 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
-  const int items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
-  // K splits: about two CTAs per SM in total (one resident at a time), never fewer than 4 pixel tiles per CTA
-  const int target = 2 * sm_count();
-  int splits = (target + items / 2) / items;
-  int max_splits = p.total_tiles / 4;
-  if (max_splits < 1) max_splits = 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
-  plan->grid = items * splits;
+  p.items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
+  p.total_units = 1LL * p.items * p.total_tiles;
+  // one CTA per SM, each an equal share of the flattened (item, tile) space; never more CTAs than units
+  p.grid = static_cast<int>(p.total_units < sm_count() ? p.total_units : sm_count());
+  int slots = 1;
+  for (int item = 0; item < p.items; ++item) {
+    const long long u0 = 1LL * item * p.total_tiles;
+    const int parts = sk_owner(p.total_units, p.grid, u0 + p.total_tiles - 1) - sk_owner(p.total_units, p.grid, u0) + 1;
+    if (parts > slots) slots = parts;
+  }
+  p.slots = slots;
+  plan->grid = p.grid;
   plan->smem = 1024 + p.stages * p.stage_bytes + 256;
-  plan->ws_bytes = 1LL * splits * taps * x.c * dy.c * 4;
+  plan->ws_bytes = 1LL * slots * taps * x.c * dy.c * 4;
   return CVB_OK;
 }
 
@@ -382,9 +434,14 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
   int bci = 32;
   while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((x.c + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
+  if (plan.p.slots > 1) {
+    const long long n4 = 1LL * taps * x.c * dy.c / 4;
+    wgrad_partsum_kernel<<<ew_grid(n4, 256, 16), 256, 0, st>>>(plan.p.ws, plan.p, plan.BN);
+    CVB_LAUNCH_CHECK();
+  }
   dim3 rgrid((dy.c + 31) / 32, (x.c + bci - 1) / bci);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, plan.p.splits, taps, x.c, dy.c,
-                                                                          cout, cin_eff, bci, dw);
+  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, x.c, dy.c, cout, cin_eff,
+                                                                          bci, dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -175,7 +175,7 @@ def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None, algo_flops=None):
         workspace = torch.empty(conv3x3_wgrad_workspace_bytes(x, dy, taps), dtype=torch.uint8, device=x.device)
     if algo_flops is None:
         algo_flops = 2.0 * taps * x.shape[3] * dy.shape[3] * dy.shape[0] * dy.shape[1] * dy.shape[2]
-    _call("conv3x3_wgrad", 2, ("flops", algo_flops, f"{tuple(x.shape)}->{dy.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
+    _call("conv3x3_wgrad", 3, ("flops", algo_flops, f"{tuple(x.shape)}->{dy.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
           cout, cin, _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     return dw
 
