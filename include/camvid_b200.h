@@ -81,6 +81,18 @@ CVB_API int cvb_pack_weights_fprop(const float* w, int cout, int cin, int taps, 
  * dst[ci][tap'][co] = w[co][ci][2-r][2-s], tap' = r*3+s, ci padded to cin_pad, co to cout_pad. */
 CVB_API int cvb_pack_weights_dgrad(const float* w, int cout, int cin, int cout_pad, int cin_pad, void* dst, void* stream);
 
+/* All 3x3 layers of a network in ONE launch (the optimizer touches every weight every step): for each entry reads the
+ * OIHW fp32 tensor once and writes both GEMM operands, dst_fprop as cvb_pack_weights_fprop(taps=9) and dst_dgrad as
+ * cvb_pack_weights_dgrad (dst_dgrad may be 0). `table` is a DEVICE array of `count` entries. */
+typedef struct {
+  const float* w;      /* [cout][cin][3][3] fp32 */
+  void* dst_fprop;     /* bf16 [cout_pad][9][cin_pad] */
+  void* dst_dgrad;     /* bf16 [cin_pad][9][cout_pad] or NULL */
+  int64_t cout, cin, cout_pad, cin_pad;
+  int64_t reserved;
+} cvb_pack_entry;
+CVB_API int cvb_pack_weights_batch(const cvb_pack_entry* table, int count, int max_cout_pad, int max_cin_pad, void* stream);
+
 /* Epilogue selection for cvb_conv3x3_fprop. */
 typedef struct {
   /* train mode: per-CTA partial sums for BatchNorm batch statistics, fp32 [cvb_conv_stat_rows()][2][y.c]

@@ -41,6 +41,7 @@ SIGNATURES = {
     "cvb_im2col3x3_nchw_f32": (_I, [_P, _I, View, _P]),
     "cvb_pack_weights_fprop": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "cvb_pack_weights_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "cvb_pack_weights_batch": (_I, [_P, _I, _I, _I, _P]),
     "cvb_conv_stat_rows": (_I, []),
     "cvb_conv3x3_fprop": (_I, [View, _P, _I, View, ctypes.POINTER(ConvEpilogue), _P]),
     "cvb_conv3x3_wgrad_workspace_bytes": (_L, [View, View, _I]),

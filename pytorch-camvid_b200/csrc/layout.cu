@@ -117,6 +117,35 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int cout, int c
   }
 }
 
+// One brick = 32 output x 32 input channels x 9 taps of one layer: read once (288 contiguous floats per output channel),
+// transposed through shared memory into both packed operands with 64-byte contiguous bf16 runs.
+__global__ void __launch_bounds__(256) pack_w_batch_kernel(const cvb_pack_entry* __restrict__ table) {
+  __shared__ float tile[32][289];
+  const cvb_pack_entry e = table[blockIdx.z];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  if (co0 >= e.cout_pad || ci0 >= e.cin_pad) return;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int cin = static_cast<int>(e.cin), cout = static_cast<int>(e.cout);
+  for (int r = wq; r < 32; r += 8) {
+    const int co = co0 + r;
+    for (int k = lane; k < 288; k += 32) {
+      const int ci = ci0 + k / 9;
+      tile[r][k] = (co < cout && ci < cin) ? __ldg(e.w + (static_cast<long long>(co) * cin + ci0) * 9 + k) : 0.f;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* df = static_cast<__nv_bfloat16*>(e.dst_fprop);
+  __nv_bfloat16* dd = static_cast<__nv_bfloat16*>(e.dst_dgrad);
+  const int cin_pad = static_cast<int>(e.cin_pad), cout_pad = static_cast<int>(e.cout_pad);
+  for (int q = wq; q < 288; q += 8) {  // (row, tap) pairs; lane = the contiguous channel
+    const int r = q / 9, tap = q - r * 9;
+    // fprop operand [co][tap][ci]: row = output channel, lane = input channel
+    df[(static_cast<long long>(co0 + r) * 9 + tap) * cin_pad + ci0 + lane] = __float2bfloat16_rn(tile[r][lane * 9 + tap]);
+    // dgrad operand [ci][tap'][co] = w[co][ci][8 - tap']: row = input channel, lane = output channel
+    if (dd) dd[(static_cast<long long>(ci0 + r) * 9 + tap) * cout_pad + co0 + lane] = __float2bfloat16_rn(tile[lane][r * 9 + (8 - tap)]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) zero_view_kernel(View v) {
   const int CV = v.c >> 3;
   const unsigned total = 1u * v.n * v.h * v.w * CV;
@@ -188,6 +217,17 @@ extern "C" int cvb_pack_weights_dgrad(const float* w, int cout, int cin, int cou
   long long total = 1LL * cin_pad * 9 * cout_pad;
   pack_w_dgrad_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin, cout_pad, cin_pad, static_cast<__nv_bfloat16*>(dst));
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_pack_weights_batch(const cvb_pack_entry* table, int count, int max_cout_pad, int max_cin_pad,
+                                      void* stream) {
+  CVB_REQUIRE(table && count > 0 && count <= 65535, CVB_ERR_INVALID_ARG, "pack_weights_batch: bad table");
+  CVB_REQUIRE(max_cout_pad > 0 && max_cin_pad > 0 && (max_cout_pad % 32) == 0 && (max_cin_pad % 32) == 0,
+              CVB_ERR_INVALID_ARG, "pack_weights_batch: padded extents must be positive multiples of 32");
+  dim3 grid(max_cout_pad / 32, max_cin_pad / 32, count);
+  pack_w_batch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

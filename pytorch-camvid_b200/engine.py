@@ -163,6 +163,28 @@ class Plan:
             b.g_end = off
         self.flat_size = off
 
+    def pack_weights(self):
+        """Refreshes the bf16 GEMM operands of every block whose fp32 weight changed (the optimizer bumps the version
+        every step): all 3x3 layers in one launch, the im2col'd first layer separately."""
+        stale = [b for b in self.blocks if b._weight_key() != b.wf_version]
+        if not stale:
+            return
+        batch = [b for b in stale if b.taps == 9]
+        if batch:
+            ptrs = tuple(b.conv.weight.data_ptr() for b in batch)
+            if getattr(self, "_pack_key", None) != ptrs:
+                self._pack_tab = ops.pack_table([(b.conv.weight.detach(), b.wf, b.wd, b.cout_pad, b.cin_pad)
+                                                 for b in batch], self.device)
+                self._pack_key = ptrs
+                self._pack_dims = (max(b.cout_pad for b in batch), max(b.cin_pad for b in batch),
+                                   sum(b.conv.weight.numel() * 4 + b.wf.numel() * 2 + b.wd.numel() * 2 for b in batch))
+            ops.pack_weights_batch(self._pack_tab, *self._pack_dims)
+            for b in batch:
+                b.wf_version = b.wd_version = b._weight_key()
+        for b in stale:
+            if b.taps != 9:
+                b._pack_f()
+
     def param_list(self):
         out = []
         for b in self.blocks:
@@ -269,6 +291,7 @@ class UNetPlan(Plan):
         self.finish()
 
     def forward(self, x, train):
+        self.pack_weights()
         ops.im2col3x3(x, self.cols)
         for l, (b0, b1) in enumerate(self.enc):
             if train:
@@ -375,6 +398,7 @@ class SegNetPlan(Plan):
         self.finish()
 
     def forward(self, x, train):
+        self.pack_weights()
         ops.im2col3x3(x, self.cols)
         for st in self.stages:
             bl = st["blocks"]

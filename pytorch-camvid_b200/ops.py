@@ -143,6 +143,22 @@ def pack_weights_dgrad(w, cout_pad, cin_pad, out=None):
     return out
 
 
+def pack_table(entries, device):
+    """Device table for pack_weights_batch. entries: (w fp32 OIHW, dst_fprop, dst_dgrad or None, cout_pad, cin_pad)."""
+    rows = []
+    for w, df, dd, cout_pad, cin_pad in entries:
+        _f32(w, "pack_table.w")
+        rows.append([w.data_ptr(), df.data_ptr(), dd.data_ptr() if dd is not None else 0, w.shape[0], w.shape[1],
+                     cout_pad, cin_pad, 0])
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def pack_weights_batch(table, max_cout_pad, max_cin_pad, nbytes):
+    """One launch packing every 3x3 layer's fprop + dgrad operands (cvb_pack_entry table on the device)."""
+    _call("pack_weights_batch", 1, ("bytes", float(nbytes)), _lib.load().cvb_pack_weights_batch, _ptr(table),
+          table.shape[0], max_cout_pad, max_cin_pad, _stream())
+
+
 def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False, algo_flops=None):
     """y = conv(x, wpack). Optional epilogues: BN statistics partials (train) or folded scale/shift(+ReLU) (eval).
     algo_flops: FLOPs of the un-padded convolution (roofline accounting); default = the padded GEMM's."""

@@ -340,3 +340,21 @@ def test_confusion_matrix_bit_exact(ops, cuda):
     pred2 = torch.empty_like(pred)
     ops.argmax_confusion_nhwc(lg, c, gt, cm, pred2)
     assert torch.equal(pred2, to_nchw_f32(lg[..., :c]).argmax(1))
+
+
+def test_pack_weights_batch_equals_single_layer_packers(ops, cuda):
+    """One-launch packing of several layers == cvb_pack_weights_fprop / _dgrad per layer, bit for bit (incl. padding)."""
+    shapes = [(64, 64), (12, 64), (128, 64), (256, 192)]  # (cout, cin); 12 -> padded to 64 output channels
+    ws = [_rand((co, ci, 3, 3), cuda, 40 + i) for i, (co, ci) in enumerate(shapes)]
+    entries, singles = [], []
+    for w in ws:
+        co_p, ci_p = ops.pad64(w.shape[0]), ops.pad64(w.shape[1])
+        df = torch.full((co_p, 9 * ci_p), 7.0, dtype=torch.bfloat16, device=cuda)
+        dd = torch.full((ci_p, 9 * co_p), 7.0, dtype=torch.bfloat16, device=cuda)
+        entries.append((w, df, dd, co_p, ci_p))
+        singles.append((ops.pack_weights_fprop(w, 9, co_p, ci_p), ops.pack_weights_dgrad(w, co_p, ci_p)))
+    table = ops.pack_table(entries, cuda)
+    ops.pack_weights_batch(table, max(e[3] for e in entries), max(e[4] for e in entries), 0)
+    torch.cuda.synchronize()
+    for (w, df, dd, _, _), (sf, sd) in zip(entries, singles):
+        assert torch.equal(df, sf) and torch.equal(dd, sd), tuple(w.shape)
