@@ -195,77 +195,100 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int 
 // ---------------------------------------------------------------------------------------------------------------
 // apply kernels
 // ---------------------------------------------------------------------------------------------------------------
+// Elementwise kernels: a thread's 8-channel group is the same in every iteration whenever the grid stride is a
+// multiple of C/8 (always for the power-of-two widths of these networks), so the per-channel vectors are loaded once
+// into registers (HOIST); otherwise they are re-read from L1 per element.
+template <bool HOIST>
 __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(View y, View a, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift) {
   const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
   const unsigned stride = gridDim.x * kThreads;
-  // two independent elements per iteration (both loads issued before either store)
-  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += 2 * stride) {
-    const unsigned i2 = i + stride;
-    const bool has2 = i2 < total;
-    unsigned pix, cv, pix2 = 0, cv2 = 0;
-    split_cv(y, i, pix, cv);
-    if (has2) split_cv(y, i2, pix2, cv2);
-    uint4 u = ldg16(y.p + poff(y, pix) + cv * 8), u2 = make_uint4(0, 0, 0, 0);
-    if (has2) u2 = ldg16(y.p + poff(y, pix2) + cv2 * 8);
-    float f[8], sc[8], sh[8];
-    unpack8(u, f);
-    ld8f(scale + cv * 8, sc);
-    ld8f(shift + cv * 8, sh);
+  float sc[8], sh[8];
+  if (HOIST) {
+    unsigned pix0, cv0;
+    split_cv(y, blockIdx.x * kThreads + threadIdx.x, pix0, cv0);
+    ld8f(scale + cv0 * 8, sc);
+    ld8f(shift + cv0 * 8, sh);
+  }
+  // four independent elements per iteration: all loads are issued before the first store
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += 4 * stride) {
+    uint4 u[4];
+    unsigned pix[4], cv[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-    stg16(a.p + poff(a, pix) + cv * 8, pack8(f));
-    if (has2) {
-      unpack8(u2, f);
-      ld8f(scale + cv2 * 8, sc);
-      ld8f(shift + cv2 * 8, sh);
+    for (int q = 0; q < 4; ++q) {
+      const unsigned iq = i + q * stride;
+      pix[q] = 0xffffffffu;
+      if (iq < total) {
+        split_cv(y, iq, pix[q], cv[q]);
+        u[q] = ldg16(y.p + poff(y, pix[q]) + cv[q] * 8);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pix[q] == 0xffffffffu) continue;
+      float f[8];
+      unpack8(u[q], f);
+      if (!HOIST) {
+        ld8f(scale + cv[q] * 8, sc);
+        ld8f(shift + cv[q] * 8, sh);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-      stg16(a.p + poff(a, pix2) + cv2 * 8, pack8(f));
+      stg16(a.p + poff(a, pix[q]) + cv[q] * 8, pack8(f));
     }
   }
 }
 
-__device__ __forceinline__ uint4 bn_bwd_elem(const uint4& uy, const uint4& ud, const float* __restrict__ scale,
-                                             const float* __restrict__ shift, const float* __restrict__ coef,
-                                             int c_pad, unsigned cv) {
-  float fy[8], fd[8], sc[8], sh[8], c0[8], c1[8], c2[8], o[8];
-  unpack8(uy, fy);
-  unpack8(ud, fd);
-  ld8f(scale + cv * 8, sc);
-  ld8f(shift + cv * 8, sh);
-  ld8f(coef + cv * 8, c0);
-  ld8f(coef + c_pad + cv * 8, c1);
-  ld8f(coef + 2 * c_pad + cv * 8, c2);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
-    o[j] = fmaf(g, c0[j], fmaf(fy[j], c1[j], c2[j]));
-  }
-  return pack8(o);
-}
-
+template <bool HOIST>
 __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, View y, View dy,
                                                                       const float* __restrict__ scale,
                                                                       const float* __restrict__ shift,
                                                                       const float* __restrict__ coef, int c_pad) {
   const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
   const unsigned stride = gridDim.x * kThreads;
+  float sc[8], sh[8], c0[8], c1[8], c2[8];
+  if (HOIST) {
+    unsigned pix0, cv0;
+    split_cv(y, blockIdx.x * kThreads + threadIdx.x, pix0, cv0);
+    ld8f(scale + cv0 * 8, sc);
+    ld8f(shift + cv0 * 8, sh);
+    ld8f(coef + cv0 * 8, c0);
+    ld8f(coef + c_pad + cv0 * 8, c1);
+    ld8f(coef + 2 * c_pad + cv0 * 8, c2);
+  }
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += 2 * stride) {
-    const unsigned i2 = i + stride;
-    const bool has2 = i2 < total;
-    unsigned pix, cv, pix2 = 0, cv2 = 0;
-    split_cv(y, i, pix, cv);
-    if (has2) split_cv(y, i2, pix2, cv2);
-    const uint4 uy = ldg16(y.p + poff(y, pix) + cv * 8);
-    const uint4 ud = ldg16(da.p + poff(da, pix) + cv * 8);
-    uint4 uy2 = make_uint4(0, 0, 0, 0), ud2 = uy2;
-    if (has2) {
-      uy2 = ldg16(y.p + poff(y, pix2) + cv2 * 8);
-      ud2 = ldg16(da.p + poff(da, pix2) + cv2 * 8);
+    uint4 uy[2], ud[2];
+    unsigned pix[2], cv[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const unsigned iq = i + q * stride;
+      pix[q] = 0xffffffffu;
+      if (iq < total) {
+        split_cv(y, iq, pix[q], cv[q]);
+        uy[q] = ldg16(y.p + poff(y, pix[q]) + cv[q] * 8);
+        ud[q] = ldg16(da.p + poff(da, pix[q]) + cv[q] * 8);
+      }
     }
-    stg16(dy.p + poff(dy, pix) + cv * 8, bn_bwd_elem(uy, ud, scale, shift, coef, c_pad, cv));
-    if (has2) stg16(dy.p + poff(dy, pix2) + cv2 * 8, bn_bwd_elem(uy2, ud2, scale, shift, coef, c_pad, cv2));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (pix[q] == 0xffffffffu) continue;
+      if (!HOIST) {
+        ld8f(scale + cv[q] * 8, sc);
+        ld8f(shift + cv[q] * 8, sh);
+        ld8f(coef + cv[q] * 8, c0);
+        ld8f(coef + c_pad + cv[q] * 8, c1);
+        ld8f(coef + 2 * c_pad + cv[q] * 8, c2);
+      }
+      float fy[8], fd[8], o[8];
+      unpack8(uy[q], fy);
+      unpack8(ud[q], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = fmaf(fy[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+        o[j] = fmaf(g, c0[j], fmaf(fy[j], c1[j], c2[j]));
+      }
+      stg16(dy.p + poff(dy, pix[q]) + cv[q] * 8, pack8(o));
+    }
   }
 }
 
@@ -343,8 +366,11 @@ extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* sh
   CVB_REQUIRE(fits_u32(y), CVB_ERR_UNSUPPORTED, "bn_relu_apply: view too large for 32-bit indexing");
   CVB_REQUIRE(scale && shift, CVB_ERR_INVALID_ARG, "bn_relu_apply: null scale/shift");
   long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
-  bn_relu_apply_kernel<<<ew_grid((total + 1) / 2, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      to_dev(y), to_dev(a), scale, shift);
+  const int grid = ew_grid((total + 3) / 4, kThreads);
+  if (kThreads % (y.c / 8) == 0)
+    bn_relu_apply_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift);
+  else
+    bn_relu_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -361,8 +387,13 @@ extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale
   CVB_REQUIRE(fits_u32(y), CVB_ERR_UNSUPPORTED, "bn_bwd_apply: view too large for 32-bit indexing");
   CVB_REQUIRE(scale && shift && coef, CVB_ERR_INVALID_ARG, "bn_bwd_apply: null pointer");
   long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
-  bn_relu_bwd_apply_kernel<<<ew_grid((total + 1) / 2, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+  const int grid = ew_grid((total + 1) / 2, kThreads);
+  if (kThreads % (y.c / 8) == 0)
+    bn_relu_bwd_apply_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+  else
+    bn_relu_bwd_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/camvid_b200.h"
 
@@ -58,6 +59,12 @@ inline bool same_shape(const cvb_view& a, const cvb_view& b) {
 
 // Grid for grid-stride elementwise kernels: enough CTAs to fill the machine a few times over, never more than needed.
 inline int ew_grid(int64_t items, int threads, int per_sm = 8) {
+  static int env_per_sm = -1;  // development knob: CVB_EW_PER_SM overrides the resident-blocks-per-SM target
+  if (env_per_sm < 0) {
+    const char* e = getenv("CVB_EW_PER_SM");
+    env_per_sm = e ? atoi(e) : 0;
+  }
+  if (env_per_sm > 0) per_sm = env_per_sm;
   int64_t need = (items + threads - 1) / threads;
   int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
   return static_cast<int>(need < 1 ? 1 : (need < cap ? need : cap));

@@ -42,9 +42,18 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(View x, View a, V
   const int CV = x.c >> 3;
   const int HO = (x.h + 1) >> 1, WO = (x.w + 1) >> 1;
   const unsigned total = 1u * x.n * HO * WO * CV;
+  // a thread keeps its channel group across iterations when the grid stride is a multiple of CV: load scale / shift once
+  const bool hoist = FUSE_BN && (kThreads % CV) == 0;
+  float sc[8], sh[8];
+  if (hoist) {
+    const int cv0 = static_cast<int>((blockIdx.x * kThreads + threadIdx.x) % CV);
+    ld8f(scale + cv0 * 8, sc);
+    ld8f(shift + cv0 * 8, sh);
+  }
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-    int cv = static_cast<int>(i % CV);
-    unsigned t = i / CV;
+    unsigned t, cvu;
+    split_cv(x, i, t, cvu);
+    const int cv = static_cast<int>(cvu);
     int wo = static_cast<int>(t % WO);
     t /= WO;
     int ho = static_cast<int>(t % HO);
@@ -52,17 +61,24 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(View x, View a, V
     const int h0 = 2 * ho, w0 = 2 * wo;
     const bool hv = (h0 + 1) < x.h, wv = (w0 + 1) < x.w;
     float v[4][8];
-    float sc[8], sh[8];
-    if (FUSE_BN) {
+    if (FUSE_BN && !hoist) {
       ld8f(scale + cv * 8, sc);
       ld8f(shift + cv * 8, sh);
+    }
+    // all window loads first, then the arithmetic and the stores
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int dh = k >> 1, dw = k & 1;
+      const bool valid = (dh == 0 || hv) && (dw == 0 || wv);
+      if (valid) raw[k] = ldg16(x.p + voff(x, n, h0 + dh, w0 + dw) + cv * 8);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int dh = k >> 1, dw = k & 1;
       const bool valid = (dh == 0 || hv) && (dw == 0 || wv);
       if (valid) {
-        unpack8(ldg16(x.p + voff(x, n, h0 + dh, w0 + dw) + cv * 8), v[k]);
+        unpack8(raw[k], v[k]);
         if (FUSE_BN) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[k][j] = fmaxf(fmaf(v[k][j], sc[j], sh[j]), 0.f);
