@@ -59,6 +59,23 @@ __host__ __device__ inline int sk_owner(long long U, int G, long long u) {  // t
   return c;
 }
 
+// Issues every K slice of one pixel tile for ACCS accumulators (compile-time: no per-MMA predication; a k-step is one
+// 32-bit add on each descriptor low word).
+template <int BN, int ACCS>
+__device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t x_lo, uint32_t d_lo, const uint32_t (&acc_lo)[kMaxAccs],
+                                           int slices, uint32_t first) {
+  constexpr uint32_t idesc = idesc_bf16_f32(128, BN, true, true);
+  constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive tile rows of the patch
+  constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy tile rows are dense
+#pragma unroll 1
+  for (int s = 0; s < slices; ++s) {
+    const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
+    const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
+#pragma unroll
+    for (int j = 0; j < ACCS; ++j) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
@@ -138,9 +155,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
-    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, true, true);
-    constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive tile rows of the patch
-    constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy tile rows are dense
     const uint32_t x_lo0 = desc_lo(smem_u32(smem), 0);
     const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * kWPatchStride, kWDyBytes);
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
@@ -180,12 +194,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t x_lo = x_lo0 + stage * stage_lo, d_lo = d_lo0 + stage * stage_lo;
         const uint32_t first = tile != tile_begin ? 1u : 0u;
         if (elect_one()) {
-          for (int s = 0; s < slices; ++s) {
-            const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
-            const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
-#pragma unroll
-            for (int j = 0; j < kMaxAccs; ++j)
-              if (j < accs) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+          switch (accs) {
+            case 1: issue_tile<BN, 1>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 2: issue_tile<BN, 2>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 3: if (3 * BN <= 512) issue_tile<BN, 3>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 4: if (4 * BN <= 512) issue_tile<BN, 4>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 5: if (5 * BN <= 512) issue_tile<BN, 5>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 6: if (6 * BN <= 512) issue_tile<BN, 6>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 7: if (7 * BN <= 512) issue_tile<BN, 7>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            default: if (8 * BN <= 512) issue_tile<BN, 8>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
           }
           umma_commit(&empty[stage]);
         }

@@ -14,7 +14,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 }
 
 template <int N, int TS>
-__global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int a_rows_stride) {
+__global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int a_rows_stride, int mn) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t mbar;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int a_
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = slot;
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = idesc_bf16_f32(128, N, false, false);
+    const uint32_t idesc = mn ? idesc_bf16_f32(128, N, true, true) : idesc_bf16_f32(128, N, false, false);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 65536);
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int a_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (TS) umma_ts(tm, tm + 256 + k * 8, smem_desc_sw128(b0 + k * 32, 16, 1024), idesc, 1u);
+        else if (mn) umma_bf16(tm, smem_desc_sw128(aa + k * 2048, 8192, 1024), smem_desc_sw128(b0 + k * 2048, 8192, 1024), idesc, 1u);
         else umma_bf16(tm, smem_desc_sw128(aa + k * 32, 16, 1024), smem_desc_sw128(b0 + k * 32, 16, 1024), idesc, 1u);
       }
     }
@@ -49,21 +50,24 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int a_
 }
 
 template <int N, int TS>
-void run(const char* tag, long long* d, int grid) {
+void run(const char* tag, long long* d, int grid, int mn = 0) {
   cudaFuncSetAttribute(rate<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
-  for (int rep = 0; rep < 2; ++rep) rate<N, TS><<<grid, 128, 100 * 1024>>>(d, iters, 0);
+  for (int rep = 0; rep < 2; ++rep) rate<N, TS><<<grid, 128, 100 * 1024>>>(d, iters, 0, mn);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("%s N=%d grid=%d: %s  %.1f clk per MMA (ideal %d)\n", tag, N, grid, cudaGetErrorString(e),
+  printf("%s mn=%d N=%d grid=%d: %s  %.1f clk per MMA (ideal %d)\n", tag, mn, N, grid, cudaGetErrorString(e),
          double(h) / (iters * 4), N / 2);
 }
 
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
-  for (int grid : {1, 148}) {
+  for (int grid : {148}) {
+    run<64, 0>("SS", d, grid, 1);
+    run<128, 0>("SS", d, grid, 1);
+    run<256, 0>("SS", d, grid, 1);
     run<64, 0>("SS", d, grid);
     run<128, 0>("SS", d, grid);
     run<256, 0>("SS", d, grid);
