@@ -63,6 +63,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def traffic_from_profiles(kernel):
+    """DRAM bytes per launch of a kernel family from the committed ncu capture (profiles/traffic.json), else None.
+    Only meaningful for the workload the capture was taken on (UNet 16x3x360x480)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return round(json.load(open(path))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
@@ -322,11 +332,14 @@ def run_b200(args):
         barrier()
         ops.profile(False)
         agg = {}
+        algo_bytes = {}
         for what, work, a, b in rec:
             d = agg.setdefault(what, [0.0, 0.0, 0, work[0]])
             d[0] += a.elapsed_time(b) * 1e-3
             d[1] += work[1]
             d[2] += 1
+            if len(work) > 3:
+                algo_bytes[what] = algo_bytes.get(what, 0.0) + work[3]
         step_s = sum(d[0] for d in agg.values()) / ksteps
         for what, (sec, amount, n, kind) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             if kind == "flops":
@@ -341,7 +354,9 @@ def run_b200(args):
             roofline = {"kernel": "conv_fprop_kernel<BN> (forward + data-gradient convs)", "bound": "tensor",
                         "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s", "frac": top["frac"],
                         "peak_source": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)",
-                        "frac_of_burst_peak": round(top["achieved"] / pk["tf_burst"], 4), "traffic": None,
+                        "frac_of_burst_peak": round(top["achieved"] / pk["tf_burst"], 4),
+                        "traffic": traffic_from_profiles("conv3x3_fprop"),
+                        "algorithmic_bytes_per_launch": round(algo_bytes.get("conv3x3_fprop", 0.0) / max(agg["conv3x3_fprop"][2], 1)),
                         "avg_launch_us": top["avg_us"], "launches_per_step": top["launches_per_step"],
                         "share_of_step": top["share_of_step"]}
 

@@ -281,6 +281,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ty_ = rem / p.TW;
     const int tx_ = rem - ty_ * p.TW;
     const bool row_in_box = row < p.TN * thw;
+    // A single 64-wide channel tile (the im2col'd first layer): per-thread statistic accumulators, reduced across lanes
+    // once per kernel (see the halo kernel); otherwise the per-tile shuffle reduction into this warp's shared-memory row.
+    constexpr int kRegCh = BN == 64 ? 64 : 1;
+    const bool reg_stats = BN == 64 && p.n_tiles == 1 && p.stat_partials != nullptr;
+    float S[kRegCh], Q[kRegCh];
+#pragma unroll
+    for (int j = 0; j < kRegCh; ++j) S[j] = Q[j] = 0.f;
+    float* my_stats = s_stats + ew * 2 * p.cout_pad;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -293,13 +301,45 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = (mt / p.tiles_h) * p.TN + tn_;
       const bool valid = row_in_box && n < p.N && h < p.H && w < p.W;
       __nv_bfloat16* dst = p.y + n * p.ysn + h * p.ysh + w * p.ysw + nt * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, dst, nt * BN, valid, lane,
-                        s_stats + ew * 2 * p.cout_pad);
+      if (BN == 64 && reg_stats) {
+#pragma unroll
+        for (int c = 0; c < kRegCh / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          epilogue_store(p, r, dst + c * 32, c * 32, valid);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              S[(c * 32 + j) % kRegCh] += v;
+              Q[(c * 32 + j) % kRegCh] = fmaf(v, v, Q[(c * 32 + j) % kRegCh]);
+            }
+          }
+        }
+      } else {
+        epilogue_rows<BN>(p, taddr, dst, nt * BN, valid, lane, my_stats);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (BN == 64 && reg_stats) {
+#pragma unroll
+      for (int c = 0; c < kRegCh / 32; ++c) {
+        float sv[32], qv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sv[j] = S[(c * 32 + j) % kRegCh];
+          qv[j] = Q[(c * 32 + j) % kRegCh];
+        }
+        const float s1 = warp_column_sum(sv, lane), s2 = warp_column_sum(qv, lane);
+        my_stats[c * 32 + lane] += s1;
+        my_stats[p.cout_pad + c * 32 + lane] += s2;
+      }
     }
   }
 

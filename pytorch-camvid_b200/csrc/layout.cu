@@ -10,16 +10,22 @@ constexpr int kThreads = 256;
 // thread = one pixel: its channels are gathered from the NCHW planes (consecutive threads read consecutive pixels of a
 // plane: coalesced) and the whole NHWC row of the pixel is written as consecutive 16-byte vectors, so a warp writes
 // 32 complete rows (no partially written 128-byte lines left for other blocks to finish).
+template <int CVT>  // CVT > 0: compile-time number of 8-channel vectors (loop fully unrolled, loads batched)
 __global__ void __launch_bounds__(kThreads) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int c_src,
                                                                           View dst) {
-  const int CV = dst.c >> 3;
+  const int CV = CVT > 0 ? CVT : (dst.c >> 3);
   const unsigned hw = static_cast<unsigned>(dst.h) * dst.w;
   const unsigned total = static_cast<unsigned>(dst.n) * hw;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     const unsigned n = i / hw, p = i - n * hw;
     const float* sp = src + static_cast<long long>(n) * c_src * hw + p;
     __nv_bfloat16* dp = dst.p + poff(dst, i);
+#pragma unroll
     for (int cv = 0; cv < CV; ++cv) {
+      if (cv * 8 >= c_src) {  // padding channels
+        stg16(dp + cv * 8, make_uint4(0, 0, 0, 0));
+        continue;
+      }
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -77,6 +83,44 @@ __global__ void __launch_bounds__(kThreads) im2col3x3_kernel(const float* __rest
         f[j] = v;
       }
       stg16(dp + cv * 8, pack8(f));
+    }
+  }
+}
+
+// The case the networks use (3 input channels -> 27 of 64 destination channels): everything is a compile-time index,
+// 27 predicated coalesced loads and eight 16-byte stores per pixel.
+__global__ void __launch_bounds__(kThreads) im2col3x3_c3_kernel(const float* __restrict__ src, View dst) {
+  const unsigned hw = static_cast<unsigned>(dst.h) * dst.w;
+  const unsigned total = static_cast<unsigned>(dst.n) * hw;
+  const int H = dst.h, W = dst.w;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned n = i / hw, p = i - n * hw;
+    const int h = static_cast<int>(p / W), w = static_cast<int>(p - (p / W) * W);
+    const float* sp = src + static_cast<long long>(n) * 3 * hw + p;
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int hh = h + r - 1, ww = w + q - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            f[ci * 9 + r * 3 + q] = __ldg(sp + static_cast<long long>(ci) * hw + (r - 1) * W + (q - 1));
+        }
+    __nv_bfloat16* dp = dst.p + poff(dst, i);
+#pragma unroll
+    for (int cv = 0; cv < 8; ++cv) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (cv < 4) {
+        u.x = pk2(f[cv * 8 + 0], f[cv * 8 + 1]);
+        u.y = pk2(f[cv * 8 + 2], f[cv * 8 + 3]);
+        u.z = pk2(f[cv * 8 + 4], f[cv * 8 + 5]);
+        u.w = pk2(f[cv * 8 + 6], f[cv * 8 + 7]);
+      }
+      stg16(dp + cv * 8, u);
     }
   }
 }
@@ -166,8 +210,12 @@ extern "C" int cvb_nchw_f32_to_nhwc_bf16(const float* src, int c_src, cvb_view d
   CVB_REQUIRE(src && c_src > 0 && c_src <= dst.c, CVB_ERR_INVALID_ARG, "nchw_to_nhwc: bad source (c_src=%d, dst.c=%d)",
               c_src, dst.c);
   long long total = 1LL * dst.n * dst.h * dst.w;
-  nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, c_src, to_dev(dst));
+  if (dst.c == 64)
+    nchw_f32_to_nhwc_bf16_kernel<8><<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, c_src, to_dev(dst));
+  else
+    nchw_f32_to_nhwc_bf16_kernel<0><<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, c_src, to_dev(dst));
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -190,8 +238,11 @@ extern "C" int cvb_im2col3x3_nchw_f32(const float* src, int c_src, cvb_view dst,
   CVB_REQUIRE(src && c_src > 0 && c_src * 9 <= dst.c, CVB_ERR_INVALID_ARG,
               "im2col3x3: 9*c_src=%d does not fit the %d destination channels", c_src * 9, dst.c);
   long long total = 1LL * dst.n * dst.h * dst.w;
-  im2col3x3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, c_src,
-                                                                                                  to_dev(dst));
+  if (c_src == 3 && dst.c == 64)
+    im2col3x3_c3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, to_dev(dst));
+  else
+    im2col3x3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, c_src,
+                                                                                                    to_dev(dst));
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -171,7 +171,8 @@ def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, rel
             raise RuntimeError("conv3x3: stat_partials too small")
     if algo_flops is None:
         algo_flops = 2.0 * taps * x.shape[3] * y.shape[3] * y.shape[0] * y.shape[1] * y.shape[2]
-    _call("conv3x3_fprop", 1, ("flops", algo_flops, f"{tuple(x.shape)}->{y.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
+    _call("conv3x3_fprop", 1, ("flops", algo_flops, f"{tuple(x.shape)}->{y.shape[3]} taps{taps}",
+                               2.0 * (x.numel() + y.numel() + wpack.numel())), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
           view(y), ctypes.byref(ep), _stream())
     return y
 

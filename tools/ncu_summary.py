@@ -21,24 +21,27 @@ def launches(path):
     rows = list(csv.reader(open(path)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h = rows[hdr]
-    kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    kn, mn, mv, mu = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
     agg = collections.OrderedDict()
-    n = 0
     for r in rows[hdr + 1:]:
         if len(r) <= mv:
             continue
         name = re.sub(r"\(.*", "", r[kn])
         v = float(r[mv].replace(",", ""))
-        v = v / 1e3 if r[mu] == "ns" else (v * 1e3 if r[mu] == "ms" else v)
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += v
-        n += 1
-    tot = sum(v[1] for v in agg.values())
+        a = agg.setdefault(name, {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
+        if r[mn] == "gpu__time_duration.sum":
+            a["n"] += 1
+            a["us"] += v / 1e3 if r[mu] in ("ns", "nsecond") else (v * 1e3 if r[mu] in ("ms", "msecond") else v)
+        elif r[mn] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[mu], 1.0)
+            a["rd" if "read" in r[mn] else "wr"] += v * scale
+    tot = sum(v["us"] for v in agg.values())
+    n = sum(v["n"] for v in agg.values())
     print(f"# ncu launch list: {n} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, serialised: compare shares)\n")
-    print("| kernel | launches | total us | share |\n|---|---|---|---|")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k[:100]}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% |")
+    print("| kernel | launches | total us | share | DRAM read MB | DRAM write MB |\n|---|---|---|---|---|---|")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        print(f"| `{k[:100]}` | {v['n']} | {v['us']:.1f} | {100 * v['us'] / tot:.1f}% | {v['rd'] / 1e6:.1f} | {v['wr'] / 1e6:.1f} |")
+    return agg
 
 
 def full(path):
