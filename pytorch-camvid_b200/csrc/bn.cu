@@ -94,27 +94,28 @@ static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finalize kernels: a block owns 32 channels; its 8 warps split the partial rows (coalesced 128-byte row reads),
+// finalize kernels: a block owns 32 channels; its 32 warps split the partial rows (coalesced 128-byte row reads),
 // accumulate in double and combine through shared memory, then warp 0 finishes the 32 channels.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 1024;
+constexpr int kFinWarps = kFinThreads / 32;
 
 __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ partials, int rows, int pstride, int ch,
                                                     bool ch_ok, double* s1_out, double* s2_out) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][kFinWarps][32];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
   if (ch_ok) {
     int r = wq;
-    for (; r + 24 < rows; r += 32) {  // 4 independent row loads in flight per thread
+    for (; r + 3 * kFinWarps < rows; r += 4 * kFinWarps) {  // 4 independent row loads in flight per thread
       float a0 = partials[(2LL * r) * pstride + ch], b0 = partials[(2LL * r + 1) * pstride + ch];
-      float a1 = partials[(2LL * (r + 8)) * pstride + ch], b1 = partials[(2LL * (r + 8) + 1) * pstride + ch];
-      float a2 = partials[(2LL * (r + 16)) * pstride + ch], b2 = partials[(2LL * (r + 16) + 1) * pstride + ch];
-      float a3 = partials[(2LL * (r + 24)) * pstride + ch], b3 = partials[(2LL * (r + 24) + 1) * pstride + ch];
+      float a1 = partials[(2LL * (r + kFinWarps)) * pstride + ch], b1 = partials[(2LL * (r + kFinWarps) + 1) * pstride + ch];
+      float a2 = partials[(2LL * (r + 2 * kFinWarps)) * pstride + ch], b2 = partials[(2LL * (r + 2 * kFinWarps) + 1) * pstride + ch];
+      float a3 = partials[(2LL * (r + 3 * kFinWarps)) * pstride + ch], b3 = partials[(2LL * (r + 3 * kFinWarps) + 1) * pstride + ch];
       s1 += (static_cast<double>(a0) + a1) + (static_cast<double>(a2) + a3);
       s2 += (static_cast<double>(b0) + b1) + (static_cast<double>(b2) + b3);
     }
-    for (; r < rows; r += 8) {
+    for (; r < rows; r += kFinWarps) {
       s1 += static_cast<double>(partials[(2LL * r) * pstride + ch]);
       s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
     }
@@ -125,7 +126,7 @@ __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ pa
   if (wq == 0) {
     s1 = s2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kFinWarps; ++q) {
       s1 += sh[0][q][lane];
       s2 += sh[1][q][lane];
     }
