@@ -54,6 +54,12 @@ CONV_CASES = [
     (2, 11, 15, 192, 64),
     (1, 8, 136, 64, 128),
     (16, 5, 7, 128, 128),
+    # halo kernel (cout <= 128, h >= 16): ragged right / bottom edges, skipped lower half, several cin chunks
+    (1, 45, 61, 64, 64),
+    (2, 33, 20, 128, 128),
+    (1, 70, 9, 256, 64),
+    (3, 17, 8, 64, 128),
+    (1, 96, 40, 192, 128),
 ]
 
 
@@ -123,6 +129,11 @@ WGRAD_CASES = [
     (1, 45, 60, 128, 256),
     (3, 22, 30, 256, 128),
     (2, 11, 15, 512, 512),
+    # ragged tiles (8 x 16 pixel tiles), odd row counts (half-filled last K slice), stream-K ranges crossing items
+    (1, 45, 61, 64, 64),
+    (1, 17, 9, 192, 64),
+    (5, 8, 8, 64, 256),
+    (1, 33, 70, 1024, 64),
 ]
 
 
