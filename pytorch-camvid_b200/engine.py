@@ -14,6 +14,13 @@ from . import ops
 from .ops import pad64
 
 
+# Backward runs every weight-gradient kernel on a side stream: it only needs (x, dy) of its own block, while the critical
+# path (dgrad -> BatchNorm backward of the previous block -> dgrad ...) alternates tensor-bound and HBM-bound kernels, so
+# the wgrad MMAs overlap the memory-bound BatchNorm / pooling / upsampling passes. bench.py turns it off for its
+# per-kernel timing pass (one stream = unambiguous event brackets).
+OVERLAP_WGRAD = True
+
+
 class Block:
     """conv3x3(pad 1, bias) + BatchNorm2d + ReLU on NHWC bf16 views."""
 
@@ -35,7 +42,12 @@ class Block:
         self.wf_version = self.wd_version = None
         self.ws_bytes = ops.conv3x3_wgrad_workspace_bytes(x, self.y, taps)
         self.flops = 2.0 * 9 * self.cin * self.cout * self.count  # algorithmic FLOPs of one pass (un-padded channels)
-        self.c_ratio = self.cout / self.cout_pad
+        # Elementwise kernels only touch the channels that exist (rounded up to the 16-byte vector): the padded output
+        # channels of y are exact zeros (zero weight rows), stay zero as dy, and are never read as activations. Matters
+        # for the 12-class output layer, whose 64-channel-padded full-resolution tensors would otherwise cost 4x.
+        self.ce = min(self.cout_pad, (self.cout + 7) // 8 * 8)
+        self.y_e, self.a_e = self.y[..., :self.ce], self.a[..., :self.ce]
+        self.c_ratio = self.cout / self.ce
         # offsets into the flat gradient buffer, assigned by the plan
         self.g_w = self.g_b = self.g_gamma = self.g_beta = None
 
@@ -75,7 +87,7 @@ class Block:
         if pool_out is not None:
             ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
         else:
-            ops.bn_relu_apply(self.y, v[2], v[3], self.a)
+            ops.bn_relu_apply(self.y_e, v[2], v[3], self.a_e)
         ops.WORK_SCALE = 1.0
 
     def forward_eval(self):
@@ -100,17 +112,26 @@ class Block:
     def backward(self, da, dx, flat):
         """da: gradient w.r.t. self.a (same view geometry); dx: view receiving the gradient w.r.t. self.x or None."""
         p, v = self.plan, self.vec
-        parts = p.parts_view(self.cout_pad)
+        parts = p.parts_view(self.ce)  # the reduce kernel lays its partial rows out with the view's channel count
         ops.WORK_SCALE = self.c_ratio
-        ops.bn_relu_bwd_reduce(da, self.y, v[2], v[3], parts, p.reduce_rows)
+        if self.ce != self.cout_pad:
+            da = da[..., :self.ce]
+        ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows)
         dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
         dbeta = flat[self.g_beta:self.g_beta + self.cout]
-        ops.bn_bwd_finalize(parts, p.reduce_rows, self.cout, self.cout_pad, self.count, self.bn.weight.detach(), v[0],
+        ops.bn_bwd_finalize(parts, p.reduce_rows, self.cout, self.ce, self.count, self.bn.weight.detach(), v[0],
                             v[1], dgamma, dbeta, self.coef)
-        ops.bn_relu_bwd_apply(da, self.y, v[2], v[3], self.coef, self.y)  # y now holds dy
+        ops.bn_relu_bwd_apply(da, self.y_e, v[2], v[3], self.coef, self.y_e)  # y now holds dy
         ops.WORK_SCALE = 1.0
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
-        ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+        if p.wstream is not None:
+            dy_ready = torch.cuda.Event()
+            dy_ready.record()
+            p.wstream.wait_event(dy_ready)
+            with torch.cuda.stream(p.wstream):
+                ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+        else:
+            ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         if self.g_b is not None:
             flat[self.g_b:self.g_b + self.cout].zero_()  # conv bias feeds a batch-stat BatchNorm: gradient is exactly 0
         if dx is not None:
@@ -130,6 +151,8 @@ class Plan:
         self.workspace = None
         self.generation = 0
         self.reducer = None  # parallel.GradReducer of the module during a backward pass (data parallelism)
+        self.wstream = None  # side stream of the weight-gradient kernels during a backward pass
+        self._wstream = None
 
     def parts_view(self, c):
         rows = self.parts.shape[0]
@@ -212,13 +235,23 @@ class Plan:
         self.reducer = self.module.__dict__.get("_cvb_reducer")
         if self.reducer is not None:
             self.reducer.begin(flat)
+        if OVERLAP_WGRAD:
+            if self._wstream is None:
+                self._wstream = torch.cuda.Stream(device=self.device)
+            self.wstream = self._wstream
+            self.wstream.wait_stream(torch.cuda.current_stream(self.device))  # flat is allocated, workspace is free
+        else:
+            self.wstream = None
         return flat
 
     def _done(self, b):
         if self.reducer is not None:
-            self.reducer.ready(b.g_w, b.g_end)
+            self.reducer.ready(b.g_w, b.g_end, also_wait=self.wstream)
 
     def _end_backward(self, flat):
+        if self.wstream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.wstream)
+            self.wstream = None
         if self.reducer is not None:
             self.reducer.finish()
             self.reducer = None
@@ -318,7 +351,7 @@ class UNetPlan(Plan):
 
     def backward(self, dlogits):
         flat = self._begin_backward()
-        ops.nchw_to_nhwc(dlogits, self.d_out_a)
+        ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.b_out.ce])
         last = self.dec[-1]
         self.b_out.backward(self.d_out_a, last["dm1"], flat)
         self._done(self.b_out)
@@ -424,7 +457,7 @@ class SegNetPlan(Plan):
 
     def backward(self, dlogits):
         flat = self._begin_backward()
-        ops.nchw_to_nhwc(dlogits, self.d_out_a)
+        ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.dstages[-1]["blocks"][-1].ce])
         for ds in reversed(self.dstages):
             bl = ds["blocks"]
             for j in range(len(bl) - 1, -1, -1):

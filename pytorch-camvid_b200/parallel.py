@@ -39,15 +39,16 @@ class GradReducer:
         if flat.is_cuda and self.side is None:
             self.side = torch.cuda.Stream(device=flat.device)
 
-    def ready(self, lo, hi):
-        """flat[lo:hi] is final on the current stream. Ranges must arrive contiguously in increasing order."""
+    def ready(self, lo, hi, also_wait=None):
+        """flat[lo:hi] is final once the work enqueued so far on the current stream (and on `also_wait`, the plan's
+        weight-gradient stream) has run. Ranges must arrive contiguously in increasing order."""
         if lo != self.hi:
             raise RuntimeError(f"camvid_b200.parallel: gradient range [{lo},{hi}) does not continue at {self.hi}")
         self.hi = hi
         if self.hi - self.lo >= self.bucket_elems:
-            self._launch()
+            self._launch(also_wait)
 
-    def _launch(self):
+    def _launch(self, also_wait=None):
         if self.hi == self.lo:
             return
         chunk = self.flat[self.lo:self.hi]
@@ -59,6 +60,8 @@ class GradReducer:
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         if chunk.is_cuda:
             self.side.wait_stream(torch.cuda.current_stream(chunk.device))
+            if also_wait is not None:
+                self.side.wait_stream(also_wait)
             with torch.cuda.stream(self.side):
                 work = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
         else:
