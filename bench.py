@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
     ap.add_argument("--height", type=int, default=360)
     ap.add_argument("--width", type=int, default=480)
+    ap.add_argument("--mode", default="train", choices=["train", "eval"],
+                    help="eval: BASELINE config 5 (forward with running statistics + argmax + confusion matrix / mIoU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
@@ -246,6 +248,12 @@ def run_b200(args):
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return tns.item()
 
+    if args.mode == "eval":
+        run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, world, rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     for i in range(max(args.warmup, 3)):
         step(dev_x[i % nbuf], dev_t[i % nbuf])
     barrier()
@@ -387,6 +395,60 @@ def run_b200(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, world, rank, dev):
+    """eval.py:50-72 / train.py:180-197 on the device: forward with BatchNorm folded into the conv epilogues, fused
+    argmax + confusion matrix, mIoU from the (all-reduced) matrix."""
+    import torch
+    from camvid_b200 import ops, parallel
+    from camvid_b200.legacy.metrics import Metrics
+    net.eval()
+    B, nbuf = args.batch, len(dev_x)
+    cm = torch.zeros(12, 12, dtype=torch.int64, device=dev)
+
+    def estep(x, t):
+        with torch.no_grad():
+            logits = net(x)
+            ops.argmax_confusion_nchw(logits, t, cm)
+
+    for i in range(max(args.warmup, 3)):
+        estep(dev_x[i % nbuf], dev_t[i % nbuf])
+    barrier()
+    cm.zero_()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        estep(dev_x[i % nbuf], dev_t[i % nbuf])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = (ops.LAUNCHES - l0) // args.steps
+    e0.record()
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        estep(host_x[i % nbuf].to(dev, non_blocking=True), host_t[i % nbuf].to(dev, non_blocking=True))
+    parallel.all_reduce_confusion(cm)
+    m = Metrics(12, 11)
+    m._confusion_matrix += cm.cpu().numpy() / 2  # both timed loops counted the same batches
+    miou = float(m.iou())
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3))
+    if rank != 0:
+        return
+    out = {"metric": metric_name(args).replace("train", "eval"), "value": world * B * args.steps / (ms * 1e-3),
+           "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args), workload=(
+               f"{args.model} eval step (forward with running statistics + argmax + confusion matrix), per-GPU batch "
+               f"{B}x3x{args.height}x{args.width}")),
+           "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": world * (host_x[0].numel() * 4 + host_t[0].numel() * 8),
+                   "d2h_bytes_per_step": 12 * 12 * 8 / args.steps, "ms_per_step": e2e_ms / args.steps},
+           "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "miou_random_init": miou}
+    print(json.dumps(out), flush=True)
 
 
 def main():
