@@ -88,6 +88,117 @@ __global__ void __launch_bounds__(kThreads) ce_nchw_f32_kernel(const float* __re
   block_accumulate(loss, cnt, out);
 }
 
+// Fast path of the two NCHW fp32 kernels for a compile-time class count and hw % 4 == 0: one thread = four consecutive
+// pixels, one 16-byte load per class plane (a warp reads 512 contiguous bytes of each plane), 32-bit indexing.
+template <int C>
+__global__ void __launch_bounds__(kThreads) ce_nchw_f32_vec4_kernel(const float* __restrict__ logits,
+                                                                     const int64_t* __restrict__ target, unsigned n,
+                                                                     unsigned hw4, long long ignore_index, double* out,
+                                                                     float* __restrict__ dlogits, float grad_scale,
+                                                                     const float* __restrict__ grad_scale_dev) {
+  const unsigned total = n * hw4;
+  const float gs = grad_scale * (grad_scale_dev ? __ldg(grad_scale_dev) : 1.f);
+  float loss = 0.f, cnt = 0.f;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned b = i / hw4, q = i - b * hw4;
+    const float4* src = reinterpret_cast<const float4*>(logits) + static_cast<size_t>(b) * C * hw4 + q;
+    float4 v[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) v[k] = __ldg(src + static_cast<size_t>(k) * hw4);
+    const longlong2 t01 = __ldg(reinterpret_cast<const longlong2*>(target) + 2 * static_cast<size_t>(i));
+    const longlong2 t23 = __ldg(reinterpret_cast<const longlong2*>(target) + 2 * static_cast<size_t>(i) + 1);
+    const long long tg[4] = {t01.x, t01.y, t23.x, t23.y};
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      float x[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) x[k] = px == 0 ? v[k].x : (px == 1 ? v[k].y : (px == 2 ? v[k].z : v[k].w));
+      const long long tgt = tg[px];
+      const bool counted = (tgt != ignore_index) && tgt >= 0 && tgt < C;
+      float mx = x[0];
+#pragma unroll
+      for (int k = 1; k < C; ++k) mx = fmaxf(mx, x[k]);
+      float se = 0.f, vt = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float e = __expf(x[k] - mx);
+        if (k == tgt) vt = x[k];
+        x[k] = e;
+        se += e;
+      }
+      const float inv = counted ? gs / se : 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float g = x[k] * inv - ((counted && k == tgt) ? gs : 0.f);
+        if (px == 0) v[k].x = g; else if (px == 1) v[k].y = g; else if (px == 2) v[k].z = g; else v[k].w = g;
+      }
+      loss += counted ? (__logf(se) + mx - vt) : 0.f;
+      cnt += counted ? 1.f : 0.f;
+    }
+    if (dlogits) {
+      float4* dst = reinterpret_cast<float4*>(dlogits) + static_cast<size_t>(b) * C * hw4 + q;
+#pragma unroll
+      for (int k = 0; k < C; ++k) dst[static_cast<size_t>(k) * hw4] = v[k];
+    }
+  }
+  block_accumulate(loss, cnt, out);
+}
+
+// per-warp private histograms (8 x c*c counters) cut shared-memory atomic contention on skewed label distributions
+__device__ __forceinline__ void cm_flush_warps(const unsigned int* hist, int cc, int64_t* cm) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < cc; i += blockDim.x) {
+    unsigned int v = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) v += hist[w * cc + i];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) argmax_confmat_nchw_vec4_kernel(const float* __restrict__ logits,
+                                                                             const int64_t* __restrict__ gt, unsigned n,
+                                                                             unsigned hw4, int64_t* __restrict__ pred,
+                                                                             int64_t* cm) {
+  __shared__ unsigned int hist[(kThreads / 32) * C * C];
+  for (int i = threadIdx.x; i < (kThreads / 32) * C * C; i += kThreads) hist[i] = 0;
+  __syncthreads();
+  unsigned int* mine = hist + (threadIdx.x >> 5) * C * C;
+  const unsigned total = n * hw4;
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned b = i / hw4, q = i - b * hw4;
+    const float4* src = reinterpret_cast<const float4*>(logits) + static_cast<size_t>(b) * C * hw4 + q;
+    float4 v[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) v[k] = __ldg(src + static_cast<size_t>(k) * hw4);
+    const longlong2 g01 = __ldg(reinterpret_cast<const longlong2*>(gt) + 2 * static_cast<size_t>(i));
+    const longlong2 g23 = __ldg(reinterpret_cast<const longlong2*>(gt) + 2 * static_cast<size_t>(i) + 1);
+    const long long gl[4] = {g01.x, g01.y, g23.x, g23.y};
+    long long arg[4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      float best = px == 0 ? v[0].x : (px == 1 ? v[0].y : (px == 2 ? v[0].z : v[0].w));
+      int a = 0;
+#pragma unroll
+      for (int k = 1; k < C; ++k) {
+        const float x = px == 0 ? v[k].x : (px == 1 ? v[k].y : (px == 2 ? v[k].z : v[k].w));
+        if (x > best || (x != x && best == best)) {  // first max; NaN is treated as maximal (torch.argmax)
+          best = x;
+          a = k;
+        }
+      }
+      arg[px] = a;
+      if (gl[px] >= 0 && gl[px] < C) atomicAdd(&mine[gl[px] * C + a], 1u);
+    }
+    if (pred) {
+      longlong2* dp = reinterpret_cast<longlong2*>(pred) + 2 * static_cast<size_t>(i);
+      dp[0] = make_longlong2(arg[0], arg[1]);
+      dp[1] = make_longlong2(arg[2], arg[3]);
+    }
+  }
+  cm_flush_warps(hist, C * C, cm);
+}
+
 __global__ void __launch_bounds__(kThreads) ce_nhwc_bf16_kernel(View logits, int c, const int64_t* __restrict__ target,
                                                                  long long ignore_index, double* out, View dl,
                                                                  bool write_grad, float grad_scale,
@@ -144,19 +255,21 @@ __device__ __forceinline__ void cm_flush(const unsigned int* hist, int cc, int64
 __global__ void __launch_bounds__(kThreads) confmat_kernel(const int64_t* __restrict__ pred,
                                                             const int64_t* __restrict__ gt, long long count, int c,
                                                             long long ignore_label, int clamp_oob, int64_t* cm) {
-  extern __shared__ unsigned int hist[];
-  for (int i = threadIdx.x; i < c * c; i += kThreads) hist[i] = 0;
+  extern __shared__ unsigned int hist[];  // [warps][c*c]
+  const int cc = c * c;
+  for (int i = threadIdx.x; i < (kThreads / 32) * cc; i += kThreads) hist[i] = 0;
   __syncthreads();
+  unsigned int* mine = hist + (threadIdx.x >> 5) * cc;
   for (long long i = 1LL * blockIdx.x * kThreads + threadIdx.x; i < count; i += 1LL * gridDim.x * kThreads) {
-    long long p = pred[i], g = gt[i];
+    long long p = __ldg(pred + i), g = __ldg(gt + i);
     if (g == ignore_label) continue;
     if (clamp_oob) {
       if (p < 0 || p >= c) p = c - 1;
       if (g < 0 || g >= c) g = c - 1;
     }
-    if (p >= 0 && p < c && g >= 0 && g < c) atomicAdd(&hist[g * c + p], 1u);
+    if (p >= 0 && p < c && g >= 0 && g < c) atomicAdd(&mine[g * c + p], 1u);
   }
-  cm_flush(hist, c * c, cm);
+  cm_flush_warps(hist, cc, cm);
 }
 
 __global__ void __launch_bounds__(kThreads) argmax_confmat_nchw_kernel(const float* __restrict__ logits,
@@ -234,6 +347,15 @@ extern "C" int cvb_softmax_ce_nchw_f32(const float* logits, const int64_t* targe
   CVB_REQUIRE(n > 0 && h > 0 && w > 0, CVB_ERR_INVALID_ARG, "softmax_ce: empty input");
   CVB_REQUIRE(c > 0 && c <= kMaxClasses, CVB_ERR_UNSUPPORTED, "softmax_ce: %d classes (max %d)", c, kMaxClasses);
   long long hw = 1LL * h * w;
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0 &&
+                       (dlogits == nullptr || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
+  if (c == 12 && hw % 4 == 0 && aligned && 1LL * n * hw < (1LL << 32)) {  // the CamVid class count, vectorised
+    const unsigned hw4 = static_cast<unsigned>(hw / 4);
+    ce_nchw_f32_vec4_kernel<12><<<ew_grid(1LL * n * hw4, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, target, static_cast<unsigned>(n), hw4, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev);
+    CVB_LAUNCH_CHECK();
+    return CVB_OK;
+  }
   ce_nchw_f32_kernel<<<ew_grid(1LL * n * hw, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, target, n, c, hw, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev);
   CVB_LAUNCH_CHECK();
@@ -276,7 +398,8 @@ extern "C" int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int6
   if (rc) return rc;
   if (count == 0) return CVB_OK;  // empty input: nothing to add (sklearn returns zeros)
   CVB_REQUIRE(pred && gt && count > 0, CVB_ERR_INVALID_ARG, "confusion_matrix: null pointer or negative count");
-  confmat_kernel<<<ew_grid(count, kThreads, 4), kThreads, c * c * sizeof(unsigned int),
+  CVB_REQUIRE(c <= 38, CVB_ERR_UNSUPPORTED, "confusion_matrix: %d classes (per-warp counters fit 38)", c);
+  confmat_kernel<<<ew_grid(count, kThreads, 8), kThreads, (kThreads / 32) * c * c * sizeof(unsigned int),
                    static_cast<cudaStream_t>(stream)>>>(pred, gt, count, c, ignore_label, clamp_oob, cm);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
@@ -289,6 +412,16 @@ extern "C" int cvb_argmax_confusion_nchw_f32(const float* logits, const int64_t*
   int rc = cm_check(c);
   if (rc) return rc;
   long long hw = 1LL * h * w;
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0 &&
+                       (pred_or_null == nullptr || (reinterpret_cast<uintptr_t>(pred_or_null) & 15) == 0);
+  if (c == 12 && hw % 4 == 0 && aligned && 1LL * n * hw < (1LL << 32)) {
+    const unsigned hw4 = static_cast<unsigned>(hw / 4);
+    argmax_confmat_nchw_vec4_kernel<12><<<ew_grid(1LL * n * hw4, kThreads, 8), kThreads, 0,
+                                          static_cast<cudaStream_t>(stream)>>>(logits, gt, static_cast<unsigned>(n), hw4,
+                                                                                pred_or_null, cm);
+    CVB_LAUNCH_CHECK();
+    return CVB_OK;
+  }
   argmax_confmat_nchw_kernel<<<ew_grid(1LL * n * hw, kThreads, 4), kThreads, c * c * sizeof(unsigned int),
                                static_cast<cudaStream_t>(stream)>>>(logits, gt, n, c, hw, pred_or_null, cm);
   CVB_LAUNCH_CHECK();

@@ -300,10 +300,11 @@ def test_bilinear2x(ops, cuda, n, h, w, c):
 
 
 # ------------------------------------------------------------------------------------------- loss / metric
+@pytest.mark.parametrize("hw", [(17, 23), (16, 24)])  # generic kernel / four-pixel vectorised 12-class kernel
 @pytest.mark.parametrize("ignore", [-100, 11])
-def test_softmax_ce(ops, cuda, ignore):
+def test_softmax_ce(ops, cuda, ignore, hw):
     torch.manual_seed(25)
-    n, c, h, w = 3, 12, 17, 23
+    n, c, (h, w) = 3, 12, hw
     logits = F.relu(torch.randn(n, c, h, w) * 2).to(cuda).requires_grad_(True)
     target = torch.randint(0, c, (n, h, w)).to(cuda)
     ref = F.cross_entropy(logits, target, ignore_index=ignore)
@@ -330,9 +331,10 @@ def test_softmax_ce(ops, cuda, ignore):
     assert torch.count_nonzero(dl2[..., c:]) == 0
 
 
-def test_confusion_matrix_bit_exact(ops, cuda):
+@pytest.mark.parametrize("hw", [(33, 47), (32, 44)])  # generic kernels / vectorised 12-class argmax kernel
+def test_confusion_matrix_bit_exact(ops, cuda, hw):
     torch.manual_seed(26)
-    n, c, h, w = 4, 12, 33, 47
+    n, c, (h, w) = 4, 12, hw
     logits = F.relu(torch.randn(n, c, h, w)).to(cuda)  # post-ReLU: argmax ties at 0 resolve to the first index
     gt = torch.randint(0, c, (n, h, w)).to(cuda)
     pred_ref = logits.argmax(1)
