@@ -16,7 +16,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               float* __restrict__ partials) {
-  extern __shared__ float red[];  // [kThreads][16]
+  __shared__ float red[kThreads * 2];
   const int CV = y.c >> 3;
   const int ppb = kThreads / CV;  // pixels handled per block iteration (CV divides kThreads, checked on host)
   const int cv = threadIdx.x % CV;
@@ -64,22 +64,22 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, co
       }
     }
   }
-  float* mine = red + threadIdx.x * 16;
+  // Cross-thread combine in eight rounds through a 2 KB buffer (round j = channel j of every 8-channel group): the
+  // kernel must stay co-resident with the weight-gradient kernel of the previous block, which leaves < 5 KB of an SM's
+  // shared memory free (engine.py runs it on a side stream under these HBM-bound passes).
+  const int C = y.c;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    mine[j] = s1[j];
-    mine[8 + j] = s2[j];
-  }
-  __syncthreads();
-  // thread t < 2*C sums column t over the ppb pixel lanes
-  const int C = y.c;
-  for (int o = threadIdx.x; o < 2 * C; o += kThreads) {
-    int which = o / C;  // 0: s1, 1: s2
-    int c = o % C;
-    int ocv = c >> 3, oj = c & 7;
-    float acc = 0.f;
-    for (int l = 0; l < ppb; ++l) acc += red[(l * CV + ocv) * 16 + which * 8 + oj];
-    partials[(1LL * blockIdx.x * 2 + which) * C + c] = acc;
+    red[threadIdx.x * 2] = s1[j];
+    red[threadIdx.x * 2 + 1] = s2[j];
+    __syncthreads();
+    if (threadIdx.x < 2 * CV) {  // thread (which, group) sums its column over the ppb pixel lanes
+      const int which = threadIdx.x / CV, ocv = threadIdx.x - which * CV;
+      float acc = 0.f;
+      for (int l = 0; l < ppb; ++l) acc += red[(l * CV + ocv) * 2 + which];
+      partials[(1LL * blockIdx.x * 2 + which) * C + ocv * 8 + j] = acc;
+    }
+    __syncthreads();
   }
 }
 
@@ -94,20 +94,21 @@ static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finalize kernels: a block owns 32 channels; its 32 warps split the partial rows (coalesced 128-byte row reads),
-// accumulate in double and combine through shared memory, then warp 0 finishes the 32 channels.
+// finalize kernels: a block owns 32 channels; its 16 warps split the partial rows (coalesced 128-byte row reads),
+// accumulate in double and combine through 4 KB of shared memory (one quantity at a time: like the reduce kernel they
+// must fit next to a resident weight-gradient CTA), then warp 0 finishes the 32 channels.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 1024;
+constexpr int kFinThreads = 512;
 constexpr int kFinWarps = kFinThreads / 32;
 
 __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ partials, int rows, int pstride, int ch,
                                                     bool ch_ok, double* s1_out, double* s2_out) {
-  __shared__ double sh[2][kFinWarps][32];
+  __shared__ double sh[kFinWarps][32];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
   if (ch_ok) {
     int r = wq;
-    for (; r + 3 * kFinWarps < rows; r += 4 * kFinWarps) {  // 4 independent row loads in flight per thread
+    for (; r + 3 * kFinWarps < rows; r += 4 * kFinWarps) {  // 8 independent loads in flight per thread
       float a0 = partials[(2LL * r) * pstride + ch], b0 = partials[(2LL * r + 1) * pstride + ch];
       float a1 = partials[(2LL * (r + kFinWarps)) * pstride + ch], b1 = partials[(2LL * (r + kFinWarps) + 1) * pstride + ch];
       float a2 = partials[(2LL * (r + 2 * kFinWarps)) * pstride + ch], b2 = partials[(2LL * (r + 2 * kFinWarps) + 1) * pstride + ch];
@@ -120,16 +121,20 @@ __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ pa
       s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
     }
   }
-  sh[0][wq][lane] = s1;
-  sh[1][wq][lane] = s2;
+  sh[wq][lane] = s1;
   __syncthreads();
   if (wq == 0) {
-    s1 = s2 = 0.0;
+    s1 = 0.0;
 #pragma unroll
-    for (int q = 0; q < kFinWarps; ++q) {
-      s1 += sh[0][q][lane];
-      s2 += sh[1][q][lane];
-    }
+    for (int q = 0; q < kFinWarps; ++q) s1 += sh[q][lane];
+  }
+  __syncthreads();
+  sh[wq][lane] = s2;
+  __syncthreads();
+  if (wq == 0) {
+    s2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < kFinWarps; ++q) s2 += sh[q][lane];
   }
   *s1_out = s1;
   *s2_out = s2;
@@ -305,7 +310,7 @@ extern "C" int cvb_bn_stats(cvb_view y, float* partials, int rows, void* stream)
   rc = reduce_launch_cfg(y, rows, &grid);
   if (rc) return rc;
   View vy = to_dev(y);
-  bn_reduce_kernel<0><<<grid, kThreads, kThreads * 16 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  bn_reduce_kernel<0><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       vy, vy, nullptr, nullptr, partials);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
@@ -322,7 +327,7 @@ extern "C" int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scal
   int grid;
   rc = reduce_launch_cfg(y, rows, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<1><<<grid, kThreads, kThreads * 16 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  bn_reduce_kernel<1><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       to_dev(y), to_dev(da), scale, shift, partials);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

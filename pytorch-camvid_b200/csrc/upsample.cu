@@ -16,48 +16,60 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
   l0 = 1.f - l1;
 }
 
-// One thread = VPT 8-channel vectors of ONE output pixel (vector indices t, t + TPP, ...: consecutive threads still
-// touch consecutive 16-byte vectors), so the source-index arithmetic is paid once per VPT vectors.
-template <int VPT>
-__global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View out, float sy, float sx) {
+// x-interpolated row: lx0 * in[y][x0] + lx1 * in[y][x1] for 8 channels
+__device__ __forceinline__ void lerp_row(const __nv_bfloat16* p0, const __nv_bfloat16* p1, float lx0, float lx1,
+                                         float (&r)[8]) {
+  const uint4 ua = ldg16(p0), ub = ldg16(p1);
+  float a[8], b[8];
+  unpack8(ua, a);
+  unpack8(ub, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = lx0 * a[j] + lx1 * b[j];
+}
+
+// One thread = one 8-channel vector of one output COLUMN, marching down a strip of `rows` output rows. The
+// x-interpolated values of the two source rows in use stay in registers: a source row is fetched once per strip (two
+// 16-byte loads) instead of once per output pixel that touches it -- about one load per store instead of four.
+// Consecutive threads = consecutive channel vectors, then consecutive columns: every access of a warp is one
+// contiguous run.
+__global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View out, float sy, float sx, int rows,
+                                                                   int strips) {
   const unsigned CV = static_cast<unsigned>(x.c) >> 3;
-  const unsigned TPP = CV / VPT;  // threads per pixel
-  const unsigned total = 1u * out.n * out.h * out.w * TPP;
+  const unsigned total = 1u * out.n * strips * out.w * CV;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-    unsigned t = i / TPP;
-    const unsigned tv = i - t * TPP;
+    unsigned t, cv;
+    split_cv(out, i, t, cv);
     const int ox = static_cast<int>(t % out.w);
     t /= out.w;
-    const int oy = static_cast<int>(t % out.h);
-    const int n = static_cast<int>(t / out.h);
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    src_index(sy, oy, x.h, y0, y1, ly0, ly1);
+    const int s = static_cast<int>(t % strips);
+    const int n = static_cast<int>(t / strips);
+    int x0, x1;
+    float lx0, lx1;
     src_index(sx, ox, x.w, x0, x1, lx0, lx1);
-    const __nv_bfloat16* p00 = x.p + voff(x, n, y0, x0);
-    const __nv_bfloat16* p01 = x.p + voff(x, n, y0, x1);
-    const __nv_bfloat16* p10 = x.p + voff(x, n, y1, x0);
-    const __nv_bfloat16* p11 = x.p + voff(x, n, y1, x1);
-    __nv_bfloat16* po = out.p + voff(out, n, oy, ox);
-    uint4 ua[VPT], ub[VPT], uc[VPT], ud[VPT];
+    const __nv_bfloat16* c0 = x.p + n * x.sn + x0 * x.sw + cv * 8;
+    const __nv_bfloat16* c1 = x.p + n * x.sn + x1 * x.sw + cv * 8;
+    __nv_bfloat16* po = out.p + n * out.sn + ox * out.sw + cv * 8;
+    float ra[8], rb[8];
+    int r = -2;  // source row held in ra; rb holds the row below it (or the same row at the bottom edge)
+    const int oy_end = min(out.h, (s + 1) * rows);
+    for (int oy = s * rows; oy < oy_end; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(sy, oy, x.h, y0, y1, ly0, ly1);
+      if (y0 != r) {
+        if (y0 == r + 1) {
 #pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      const unsigned off = (tv + v * TPP) * 8;
-      ua[v] = ldg16(p00 + off);
-      ub[v] = ldg16(p01 + off);
-      uc[v] = ldg16(p10 + off);
-      ud[v] = ldg16(p11 + off);
-    }
+          for (int j = 0; j < 8; ++j) ra[j] = rb[j];
+        } else {
+          lerp_row(c0 + y0 * x.sh, c1 + y0 * x.sh, lx0, lx1, ra);
+        }
+        lerp_row(c0 + y1 * x.sh, c1 + y1 * x.sh, lx0, lx1, rb);
+        r = y0;
+      }
+      float o[8];
 #pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      float a[8], b[8], c[8], d[8], o[8];
-      unpack8(ua[v], a);
-      unpack8(ub[v], b);
-      unpack8(uc[v], c);
-      unpack8(ud[v], d);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = ly0 * (lx0 * a[j] + lx1 * b[j]) + ly1 * (lx0 * c[j] + lx1 * d[j]);
-      stg16(po + (tv + v * TPP) * 8, pack8(o));
+      for (int j = 0; j < 8; ++j) o[j] = ly0 * ra[j] + ly1 * rb[j];
+      stg16(po + oy * out.sh, pack8(o));
     }
   }
 }
@@ -85,55 +97,81 @@ __device__ __forceinline__ int gather_taps(float scale, float inv, int in, int o
       ++cnt;
     }
   }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (k >= cnt) {
+      idx[k] = idx[0];
+      wgt[k] = 0.f;
+    }
   return cnt;
 }
 
-template <int VPT>
+// Backward, separable: one thread = one 8-channel vector of one input COLUMN and a strip of `rows` input rows. It walks
+// the output rows whose stencils touch the strip; per output row it gathers along x (the <= 6 output columns that touch
+// its input column, found once per thread) and adds the result into two rolling row accumulators (source rows y0 and
+// y0 + 1 of that output row). 4-5 loads per output row instead of 16-25 per input pixel.
 __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, View dx, float sy, float sx, float isy,
-                                                                   float isx) {
+                                                                   float isx, int rows, int strips) {
   const unsigned CV = static_cast<unsigned>(dx.c) >> 3;
-  const unsigned TPP = CV / VPT;
-  const unsigned total = 1u * dx.n * dx.h * dx.w * TPP;
+  const unsigned total = 1u * dx.n * strips * dx.w * CV;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-    unsigned t = i / TPP;
-    const unsigned tv = i - t * TPP;
+    unsigned t, cv;
+    split_cv(dx, i, t, cv);
     const int ix = static_cast<int>(t % dx.w);
     t /= dx.w;
-    const int iy = static_cast<int>(t % dx.h);
-    const int n = static_cast<int>(t / dx.h);
-    int oy[6], ox[6];
-    float wy[6], wx[6];
-    const int ny = gather_taps(sy, isy, dx.h, dout.h, iy, oy, wy);
+    const int s = static_cast<int>(t % strips);
+    const int n = static_cast<int>(t / strips);
+    int ox[6];
+    float wx[6];
     const int nx = gather_taps(sx, isx, dx.w, dout.w, ix, ox, wx);
-    float acc[VPT][8];
+    const __nv_bfloat16* src = dout.p + n * dout.sn + cv * 8;
+    __nv_bfloat16* dst = dx.p + n * dx.sn + ix * dx.sw + cv * 8;
+    const int ra = s * rows, rb = min(dx.h, ra + rows);  // owned input rows [ra, rb)
+    const int lo = max(0, static_cast<int>(floorf((ra - 1) * isy)) - 1);
+    const int hi = min(dout.h - 1, static_cast<int>(ceilf(rb * isy)) + 1);
+    float A[8], B[8];  // accumulators of input rows r and r + 1
 #pragma unroll
-    for (int v = 0; v < VPT; ++v)
+    for (int j = 0; j < 8; ++j) A[j] = B[j] = 0.f;
+    int r = ra - 1;
+    for (int oy = lo; oy <= hi; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(sy, oy, dx.h, y0, y1, ly0, ly1);
+      if (y1 < ra) continue;
+      if (y0 >= rb) break;
+      while (r < y0) {  // rows above y0 are complete
+        if (r >= ra) stg16(dst + r * dx.sh, pack8(A));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+        for (int j = 0; j < 8; ++j) {
+          A[j] = B[j];
+          B[j] = 0.f;
+        }
+        ++r;
+      }
+      const __nv_bfloat16* rowp = src + oy * dout.sh;
+      uint4 u[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      if (a >= ny) break;
-      const __nv_bfloat16* rowp = dout.p + n * dout.sn + oy[a] * dout.sh + tv * 8;
+      for (int b = 0; b < 6; ++b) u[b] = b < nx ? ldg16(rowp + ox[b] * dout.sw) : make_uint4(0u, 0u, 0u, 0u);
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
       for (int b = 0; b < 6; ++b) {
-        if (b >= nx) break;
-        const float wgt = wy[a] * wx[b];
-        const __nv_bfloat16* pp = rowp + ox[b] * dout.sw;
-        uint4 u[VPT];
+        float v[8];
+        unpack8(u[b], v);
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) u[v] = ldg16(pp + v * TPP * 8);
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(wx[b], v[j], g[j]);
+      }
+      const float la = y1 == y0 ? ly0 + ly1 : ly0, lb = y1 == y0 ? 0.f : ly1;
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-          float g[8];
-          unpack8(u[v], g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[v][j] = fmaf(wgt, g[j], acc[v][j]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        A[j] = fmaf(la, g[j], A[j]);
+        B[j] = fmaf(lb, g[j], B[j]);
       }
     }
-    __nv_bfloat16* po = dx.p + voff(dx, n, iy, ix);
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) stg16(po + (tv + v * TPP) * 8, pack8(acc[v]));
+    if (r >= ra && r < rb) stg16(dst + r * dx.sh, pack8(A));
+    if (r + 1 >= ra && r + 1 < rb) stg16(dst + (r + 1) * dx.sh, pack8(B));
+    for (int z = max(r + 2, ra); z < rb; ++z) stg16(dst + z * dx.sh, make_uint4(0u, 0u, 0u, 0u));  // untouched rows
   }
 }
 
@@ -150,6 +188,13 @@ static int up_shapes_ok(const cvb_view& x, const cvb_view& out, const char* who)
 
 static inline float ac_scale(int in, int out) { return out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f; }
 
+// rows per thread: long strips amortise the strip's first row fetches, but the grid must still fill the machine
+static int strip_rows(int n, int h, int w, int cv, int want) {
+  int rows = want;
+  while (rows > 2 && 1LL * n * ((h + rows - 1) / rows) * w * cv < 2LL * sm_count() * 2048) rows >>= 1;
+  return rows;
+}
+
 extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   int rc = check_view(x, "bilinear.x");
   if (rc) return rc;
@@ -159,14 +204,13 @@ extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   if (rc) return rc;
   CVB_REQUIRE(fits_u32(out), CVB_ERR_UNSUPPORTED, "bilinear2x_fwd: view too large for 32-bit indexing");
   const int cv = out.c / 8;
-  const int vpt = (cv % 4 == 0 && cv >= 32) ? 4 : ((cv % 2 == 0 && cv >= 16) ? 2 : 1);
-  long long total = 1LL * out.n * out.h * out.w * (cv / vpt);
+  const int rows = strip_rows(out.n, out.h, out.w, cv, 16);
+  const int strips = (out.h + rows - 1) / rows;
+  long long total = 1LL * out.n * strips * out.w * cv;
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float fsy = ac_scale(x.h, out.h), fsx = ac_scale(x.w, out.w);
-  if (vpt == 4) bilinear2x_fwd_kernel<4><<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx);
-  else if (vpt == 2) bilinear2x_fwd_kernel<2><<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx);
-  else bilinear2x_fwd_kernel<1><<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx);
+  bilinear2x_fwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -182,13 +226,12 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   float isy = sy > 0.f ? 1.f / sy : static_cast<float>(dout.h), isx = sx > 0.f ? 1.f / sx : static_cast<float>(dout.w);
   CVB_REQUIRE(fits_u32(dout), CVB_ERR_UNSUPPORTED, "bilinear2x_bwd: view too large for 32-bit indexing");
   const int cv = dx.c / 8;
-  const int vpt = (cv % 4 == 0 && cv >= 32) ? 4 : ((cv % 2 == 0 && cv >= 16) ? 2 : 1);
-  long long total = 1LL * dx.n * dx.h * dx.w * (cv / vpt);
+  const int rows = strip_rows(dx.n, dx.h, dx.w, cv, 8);
+  const int strips = (dx.h + rows - 1) / rows;
+  long long total = 1LL * dx.n * strips * dx.w * cv;
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vpt == 4) bilinear2x_bwd_kernel<4><<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx);
-  else if (vpt == 2) bilinear2x_bwd_kernel<2><<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx);
-  else bilinear2x_bwd_kernel<1><<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx);
+  bilinear2x_bwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -8,6 +8,10 @@ C ABI (ops.py). Nothing is allocated per step except the flat fp32 gradient buff
 Reference topology: models/unet.py:35-156 and models/segnet.py:19-119; one "block" is the reference's
 BasicConv2d / BasicConv (conv3x3 pad 1 + BatchNorm2d + ReLU, models/unet.py:5-17, models/segnet.py:5-17).
 """
+import itertools
+import weakref
+from typing import List
+
 import torch
 
 from . import ops
@@ -124,19 +128,23 @@ class Block:
         ops.bn_relu_bwd_apply(da, self.y_e, v[2], v[3], self.coef, self.y_e)  # y now holds dy
         ops.WORK_SCALE = 1.0
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
-        if p.wstream is not None:
-            dy_ready = torch.cuda.Event()
-            dy_ready.record()
-            p.wstream.wait_event(dy_ready)
-            with torch.cuda.stream(p.wstream):
-                ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
-        else:
-            ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         if self.g_b is not None:
             flat[self.g_b:self.g_b + self.cout].zero_()  # conv bias feeds a batch-stat BatchNorm: gradient is exactly 0
+        if p.wstream is None:
+            ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         if dx is not None:
             self._pack_d()
             ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops)
+        if p.wstream is not None:
+            # The side stream picks the weight gradient up AFTER the data gradient: started together the two tensor-bound
+            # kernels only split the SMs between them (measured: same finish time as back to back) and the HBM-bound
+            # BatchNorm passes of the next block then run alone. Started here, the weight gradient's MMAs run under
+            # those passes (they need no shared memory and co-reside with the wgrad CTAs).
+            ready = torch.cuda.Event()
+            ready.record()
+            p.wstream.wait_event(ready)
+            with torch.cuda.stream(p.wstream):
+                ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
 
 
 class Plan:
@@ -153,6 +161,8 @@ class Plan:
         self.reducer = None  # parallel.GradReducer of the module during a backward pass (data parallelism)
         self.wstream = None  # side stream of the weight-gradient kernels during a backward pass
         self._wstream = None
+        self.handle = next(_HANDLES)  # how the dispatcher ops below address this plan
+        _PLANS[self.handle] = self
 
     def parts_view(self, c):
         rows = self.parts.shape[0]
@@ -478,24 +488,70 @@ class SegNetPlan(Plan):
         return self._end_backward(flat)
 
 
-class _NetFunction(torch.autograd.Function):
-    """One autograd node for the whole network: forward/backward are the plan's kernel sequences."""
+# ---------------------------------------------------------------------------------------------------------------------
+# torch custom-op layer. The whole network is ONE dispatcher op per direction (`camvid_b200::net_forward` /
+# `camvid_b200::net_backward`, registered through torch.library with a fake (shape-only) implementation and an autograd
+# formula), so the drop-in modules are ordinary citizens of autograd AND of torch.jit.trace -- utils.visualize_network's
+# `writer.add_graph(net, tensor)` (utils.py:10-13, train.py:97-98) records one opaque node instead of failing. Plans are
+# addressed by an integer handle because dispatcher arguments are tensors and scalars.
+_PLANS = weakref.WeakValueDictionary()  # handle -> plan (the owning module keeps the plan alive)
+_HANDLES = itertools.count(1)
 
-    @staticmethod
-    def forward(ctx, x, plan, *params):
-        ctx.plan = plan
-        plan.generation += 1
-        ctx.generation = plan.generation
-        return plan.forward(x, True)
 
-    @staticmethod
-    def backward(ctx, dlogits):
-        plan = ctx.plan
-        if ctx.generation != plan.generation:
-            raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
-                               "later forward of the same module and input shape (plans own one set of buffers)")
-        flat = plan.backward(dlogits.float().contiguous())
-        return (None, None) + tuple(plan.grads_for(flat))
+def _plan_of(handle):
+    plan = _PLANS.get(handle)
+    if plan is None:
+        raise RuntimeError(f"camvid_b200: execution plan {handle} no longer exists (its module was freed)")
+    return plan
+
+
+@torch.library.custom_op("camvid_b200::net_forward", mutates_args=())
+def net_forward_op(x: torch.Tensor, params: List[torch.Tensor], plan_handle: int, train: bool) -> torch.Tensor:
+    """x fp32 NCHW -> logits fp32 NCHW. `params` (reference order: conv.weight, conv.bias, bn.weight, bn.bias per block)
+    are listed so that autograd routes their gradients; the kernels read them through the plan. Train mode also updates
+    the BatchNorm running statistics of the owning module, exactly like nn.BatchNorm2d."""
+    plan = _plan_of(plan_handle)
+    plan.generation += 1  # every forward overwrites the plan's activation buffers
+    return plan.forward(x, train)
+
+
+@net_forward_op.register_fake
+def _net_forward_fake(x, params, plan_handle, train):
+    return x.new_empty(x.shape[0], _plan_of(plan_handle).class_num, x.shape[2], x.shape[3])
+
+
+@torch.library.custom_op("camvid_b200::net_backward", mutates_args=())
+def net_backward_op(dlogits: torch.Tensor, plan_handle: int, generation: int) -> torch.Tensor:
+    """Gradients of the loss w.r.t. every entry of `params` of the matching net_forward call, as ONE flat fp32 buffer
+    (laid out in backward completion order, the unit of the data-parallel all-reduce buckets); Plan.grads_for slices it
+    into per-parameter views."""
+    plan = _plan_of(plan_handle)
+    if generation != plan.generation:
+        raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
+                           "later forward of the same module and input shape (plans own one set of buffers)")
+    return plan.backward(dlogits.float().contiguous())
+
+
+@net_backward_op.register_fake
+def _net_backward_fake(dlogits, plan_handle, generation):
+    return dlogits.new_empty(_plan_of(plan_handle).flat_size)
+
+
+def _net_setup_context(ctx, inputs, output):
+    _, _, handle, train = inputs
+    ctx.handle, ctx.train = handle, train
+    ctx.generation = _plan_of(handle).generation
+
+
+def _net_backward(ctx, dlogits):
+    if not ctx.train:
+        raise RuntimeError("camvid_b200: backward() through an eval-mode forward is not supported (BatchNorm is folded "
+                           "into the conv epilogues and nothing is saved); call module.train() first")
+    flat = net_backward_op(dlogits, ctx.handle, ctx.generation)
+    return None, _plan_of(ctx.handle).grads_for(flat), None, None
+
+
+net_forward_op.register_autograd(_net_backward, setup_context=_net_setup_context)
 
 
 def run_module(module, plan_cls, x):
@@ -517,8 +573,4 @@ def run_module(module, plan_cls, x):
     if plan is None or any(b.conv.weight.device != x.device for b in plan.blocks[:1]):
         plan = plan_cls(module, n, h, w, x.device)
         plans[key] = plan
-    if module.training:
-        if torch.is_grad_enabled():
-            return _NetFunction.apply(x, plan, *plan.param_list())
-        return plan.forward(x, True)
-    return plan.forward(x, False)
+    return net_forward_op(x, plan.param_list(), plan.handle, bool(module.training))

@@ -339,3 +339,25 @@ def test_backward_after_second_forward_fails_loudly(cvb, cuda):
     net(x.to(cuda))
     with pytest.raises(RuntimeError, match="overwritten"):
         l1.backward()
+
+
+def test_jit_trace_records_one_dispatcher_op(cvb, cuda):
+    """utils.visualize_network (utils.py:10-13; train.py:97-98) traces the TRAIN-mode module with torch.jit.trace on a
+    [1,3,480,360]-shaped tensor (IMAGE_SIZE transposed). The drop-in must trace: the network is one
+    `camvid_b200::net_forward` node, and the traced module reproduces the eager output."""
+    cutils, _ = cvb
+    net = cutils.get_model("unet", 3, 12).to(cuda).train()
+    x = torch.randn(1, 3, 48, 36, device=cuda)
+    traced = torch.jit.trace(net, x, strict=False)
+    assert "camvid_b200::net_forward" in str(traced.inlined_graph)
+    assert torch.equal(traced(x), net(x))
+
+
+def test_custom_op_schema_and_eval_backward_guard(cvb, cuda):
+    cutils, cnn = cvb
+    assert "Tensor[] params" in str(torch.ops.camvid_b200.net_forward.default._schema)
+    net = cutils.get_model("segnet", 3, 12).to(cuda).eval()
+    x, t = O.synth_batch(1, 32, 32, seed=12)
+    loss = cnn.CrossEntropyLoss()(net(x.to(cuda)), t.to(cuda))
+    with pytest.raises(RuntimeError, match="eval-mode"):
+        loss.backward()

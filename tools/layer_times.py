@@ -8,7 +8,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import camvid_b200  # noqa
-from camvid_b200 import ops
+from camvid_b200 import engine, ops
+
+engine.OVERLAP_WGRAD = False  # one stream: unambiguous event brackets
 from camvid_b200.nn import CrossEntropyLoss
 from camvid_b200.utils import get_model
 
