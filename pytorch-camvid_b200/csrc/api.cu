@@ -67,6 +67,25 @@ int make_act_tmap(CUtensorMap* out, const cvb_view& v, int box_w, int box_h, int
   return CVB_OK;
 }
 
+int make_act_tmap_rowpairs(CUtensorMap* out, const cvb_view& v, int box_w, int box_pairs) {
+  EncodeTiledFn fn = encode_fn();
+  CVB_REQUIRE(fn != nullptr, CVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  CVB_REQUIRE((v.c % 64) == 0 && (v.h % 2) == 0, CVB_ERR_UNSUPPORTED,
+              "row-pair view needs channels %% 64 == 0 and an even height (got c %d, h %d)", v.c, v.h);
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(v.c), static_cast<cuuint64_t>(v.w), 2,
+                        static_cast<cuuint64_t>(v.h / 2), static_cast<cuuint64_t>(v.n)};
+  cuuint64_t strides[4] = {static_cast<cuuint64_t>(v.sw) * 2, static_cast<cuuint64_t>(v.sh) * 2,
+                           static_cast<cuuint64_t>(v.sh) * 4, static_cast<cuuint64_t>(v.sn) * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(box_w), 1, static_cast<cuuint32_t>(box_pairs), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CVB_REQUIRE(r == CUDA_SUCCESS, CVB_ERR_CUDA, "cuTensorMapEncodeTiled(row pairs %dx%dx%dx%d box %d,%d) failed: %d",
+              v.n, v.h, v.w, v.c, box_w, box_pairs, static_cast<int>(r));
+  return CVB_OK;
+}
+
 int make_mat_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   CVB_REQUIRE(fn != nullptr, CVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");

@@ -621,6 +621,550 @@ conv_fprop_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the halo kernel (cta_group::2). In the single-CTA kernel an MMA of N = 64 reads 4 KB of A and
+// 2 KB of B from shared memory (48-60 clk at 128 B/clk) for 32 clk of tensor work: the full-resolution 64-channel
+// layers are shared-memory bound. Here two CTAs of one TPC each own an 8 x 32 pixel tile and its activation patch, each
+// loads HALF of every weight tile, and the leader issues M = 256 MMAs that span both tiles: per SM an MMA now reads
+// 4 KB + 1 KB. Everything else (patch reuse across the nine taps, per-thread BatchNorm statistics) is the kernel above.
+//   barriers: full* live in the leader (two producer arrivals, transaction bytes of both CTAs' TMA loads); empty* and
+//   tfull are signalled in both CTAs by multicast commits; tempty lives in the leader and collects the epilogue warps
+//   of both CTAs.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Halo2Cfg {
+  static constexpr int kStagesA = 3;
+  static constexpr int kStagesB = BN == 64 ? 20 : 10;
+  static constexpr int kBBytes = (BN / 2) * 128;  // this CTA's half of a weight tile
+  static constexpr int kTmemCols = 4 * BN;
+  static constexpr int kSmem = 1024 + kStagesA * kPatchStride + kStagesB * kBBytes + 4 * 2 * BN * 4 + 512;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+conv_fprop_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const FpropParams p) {
+  using Cfg = Halo2Cfg<BN>;
+  constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * kPatchStride;
+  float* s_stats = reinterpret_cast<float*>(sB + SB * Cfg::kBBytes);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(s_stats + 4 * 2 * BN);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tfull = emptyB + SB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int pair_tiles = (p.total_tiles + 1) >> 1;  // tile pair t = tiles (2t, 2t+1); an odd last tile is duplicated
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&fullA[i], 2);
+      mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(&fullB[i], 2);
+      mbar_init(&emptyB[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers and TMEM exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+  setmaxnreg_dec<40>();
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- activation-patch producer (own tile) -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tp = pair; tp < pair_tiles; tp += n_pairs) {
+        int mt = min(2 * tp + static_cast<int>(rank), p.total_tiles - 1);
+        const int w0 = (mt % p.tiles_w) * kHaloW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * kHaloH;
+        const int n0 = mt / p.tiles_h;
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          mbar_wait(&emptyA[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&fullA[stage], 2 * kPatchBytes);
+          tma_load_4d_pair(sA + stage * kPatchStride, &tmA, &fullA[stage], chunk * 64, w0 - 1, h0 - 1, n0);
+          if (rank != 0) mbar_arrive_leader(&fullA[stage]);
+          if (++stage == SA) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------- weight-tile producer (own half of the cout rows) -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tp = pair; tp < pair_tiles; tp += n_pairs) {
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyB[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&fullB[stage], 2 * Cfg::kBBytes);
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &fullB[stage], tap * p.cin_pad + chunk * 64,
+                             static_cast<int>(rank) * (BN / 2));
+            if (rank != 0) mbar_arrive_leader(&fullB[stage]);
+            if (++stage == SB) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------- MMA issuer (leader CTA only) -------------------------------
+    constexpr uint32_t idesc = idesc_bf16_f32(256, BN, false, false);
+    constexpr uint32_t a_hi = desc_hi_sw128((kHaloW + 2) * 128), b_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int t0 = 2 * tp, t1 = min(2 * tp + 1, p.total_tiles - 1);
+      const int h00 = ((t0 / p.tiles_w) % p.tiles_h) * kHaloH, h01 = ((t1 / p.tiles_w) % p.tiles_h) * kHaloH;
+      const bool two = (h00 + 16 < p.H) || (h01 + 16 < p.H);  // lower halves of both tiles below the image: skip
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * 2 * BN;
+      for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+        mbar_wait(&fullA[sa], pa);
+        const uint32_t a_st = a_lo0 + sa * (kPatchStride >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&fullB[sb], pb);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + sb * (Cfg::kBBytes >> 4);
+          const int dr = tap / 3, ds = tap - dr * 3;
+          const uint32_t a_lo = a_st + (dr * (kHaloW + 2) + ds) * 8;
+          const uint32_t first = (chunk | tap) != 0 ? 1u : 0u;
+          if (elect_one()) {
+            umma_bf16_lohi_pair(d0, a_lo, a_hi, b_lo, b_hi, idesc, first);
+            umma_bf16_lohi_pair(d0, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+            umma_bf16_lohi_pair(d0, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+            umma_bf16_lohi_pair(d0, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            if (two) {
+              constexpr uint32_t half = 16 * (kHaloW + 2) * 8;
+              umma_bf16_lohi_pair(d0 + BN, a_lo + half, a_hi, b_lo, b_hi, idesc, first);
+              umma_bf16_lohi_pair(d0 + BN, a_lo + half + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              umma_bf16_lohi_pair(d0 + BN, a_lo + half + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_bf16_lohi_pair(d0 + BN, a_lo + half + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            }
+            umma_commit_pair(&emptyB[sb]);
+          }
+          __syncwarp();
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit_pair(&emptyA[sa]);
+        __syncwarp();
+        if (++sa == SA) {
+          sa = 0;
+          pa ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit_pair(&tfull[acc]);
+      __syncwarp();
+    }
+  }
+  } else {
+    setmaxnreg_inc<232>();
+    // --------------------------------- epilogue (own tile, own TMEM) -----------------------------------
+    constexpr int CH = BN / 2;
+    const int ew = warp & 3;
+    const int cbase = ((warp - 4) >> 2) * CH;
+    const int row = ew * 32 + lane;
+    const int ty_ = row >> 3, tx_ = row & 7;
+    float S[CH], Q[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) S[j] = Q[j] = 0.f;
+    const bool want_stats = p.stat_partials != nullptr;
+    int it = 0;
+    for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int mt = 2 * tp + static_cast<int>(rank);
+      const bool real = mt < p.total_tiles;  // the duplicate of an odd last tile is computed but not stored
+      mt = min(mt, p.total_tiles - 1);
+      const int w = (mt % p.tiles_w) * kHaloW + tx_;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * kHaloH;
+      const int n = mt / p.tiles_h;
+      const int halves = (h0 + 16 < p.H) ? 2 : 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int half = 0; half < halves; ++half) {
+        const int h = h0 + half * 16 + ty_;
+        const bool valid = real && h < p.H && w < p.W;
+        __nv_bfloat16* dst = p.y + n * p.ysn + h * p.ysh + w * p.ysw + cbase;
+        const uint32_t t_a = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * 2 + half) * BN + cbase;
+#pragma unroll
+        for (int c = 0; c < CH / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_a + c * 32, r);
+          tmem_ld_wait();
+          epilogue_store(p, r, dst + c * 32, cbase + c * 32, valid);
+          if (want_stats && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              S[c * 32 + j] += v;
+              Q[c * 32 + j] = fmaf(v, v, Q[c * 32 + j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+    }
+#pragma unroll
+    for (int c = 0; c < CH / 32; ++c) {
+      float s[32], q[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s[j] = S[c * 32 + j];
+        q[j] = Q[c * 32 + j];
+      }
+      const float s1 = warp_column_sum(s, lane), s2 = warp_column_sum(q, lane);
+      s_stats[ew * 2 * BN + cbase + c * 32 + lane] = s1;
+      s_stats[ew * 2 * BN + BN + cbase + c * 32 + lane] = s2;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (p.stat_partials) {
+    float* dstp = p.stat_partials + static_cast<long long>(blockIdx.x) * 2 * p.cout_pad;
+    for (int i = threadIdx.x; i < 2 * BN; i += kHaloThreads)
+      dstp[i] = (s_stats[i] + s_stats[2 * BN + i]) + (s_stats[4 * BN + i] + s_stats[6 * BN + i]);
+  }
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still touch its barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Transposed variant for cout_pad == 64 (the full-resolution stages and every data gradient that lands on 64
+// channels). With pixels on M, an MMA reads its 128 activation rows from shared memory in ~60 clk whatever N is
+// (measured: 60 / 64 / 128 clk at N = 64 / 128 / 256), so N = 64 keeps the tensor pipe half idle. Here the roles are
+// swapped: D^T[(shift, cout)][pixel] = A[(shift, cout)][cin] * B[pixel][cin]^T with N = 256 pixels per MMA.
+//   * M = 128 = two 64-row blocks of weights. Block s holds the tap (dr - s, dc) of the activation view (dr, dc) the MMA
+//     reads, so block s accumulates the OUTPUT ROW 2i + s from the pixel rows 2i + dr: one accumulator covers two
+//     output rows per pixel-row pair, 12 views (dr = -1..2, dc = -1..1) carry the 18 (tap, shift) products (75 % of
+//     the MMA rows do useful work; taps that do not exist for a block are zero rows, fetched as an out-of-bounds TMA box).
+//   * B = a view of a ROW-PARITY patch: even image rows (dr = 0, 2) or odd ones (dr = -1, 1), 33 rows x 10 pixels, fetched
+//     once per 64-channel chunk through a 5-D tensor map (rows split into (pair, parity)); the view of (dr, dc) starts
+//     at patch row ((dr >> 1 or so) * 10 + dc + 1) with SBO = 10 pixels, like the taps of the halo kernel.
+//   * tile = 8 (w) x 64 (h) output pixels = 256 accumulator columns, double-buffered in TMEM (512 columns).
+//   * epilogue: a thread owns ONE (shift, channel) lane: BatchNorm statistics are two scalars per thread with no
+//     cross-lane work at all; stores are 2-byte, 32 lanes = 64 contiguous bytes of one pixel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTrW = 8, kTrI = 32;
+constexpr int kTrPitch = kTrW + 2;
+constexpr int kTrPatchRows = (kTrI + 1) * kTrPitch;  // 330 pixel rows of 128 B
+constexpr int kTrPatchBytes = kTrPatchRows * 128;    // 42240
+constexpr int kTrPatchStride = 43008;                // rounded up to 1 KB
+constexpr int kTrStagesP = 3, kTrStagesW = 5;
+constexpr int kTrWBytes = 128 * 128;  // [2 shifts x 64 cout][64 cin]
+constexpr int kTrThreads = 384;
+constexpr int kTrSmem = 1024 + kTrStagesP * kTrPatchStride + kTrStagesW * kTrWBytes + 8 * 2048 + 8 * 64 * 4 + 256;
+
+__device__ __forceinline__ int tr_cols(int H, int h0) {  // accumulator columns of a tile: 8 per row pair in the image
+  int icnt = min(kTrI, (H - h0 + 1) >> 1);
+  icnt = (icnt + 1) & ~1;  // N must be a multiple of 16
+  return icnt * kTrW;
+}
+
+__global__ void __launch_bounds__(kTrThreads, 1)
+conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                       const FpropParams p) {
+  constexpr int SP = kTrStagesP, SW = kTrStagesW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem;
+  uint8_t* sW = sP + SP * kTrPatchStride;
+  uint8_t* sT = sW + SW * kTrWBytes;                                // [8 epilogue warps][32 pixels][32 channels] bf16
+  float* s_stats = reinterpret_cast<float*>(sT + 8 * 2048);         // [8 epilogue warps][sum | sumsq][32 lanes]
+  uint64_t* fullP = reinterpret_cast<uint64_t*>(s_stats + 8 * 64);
+  uint64_t* emptyP = fullP + SP;
+  uint64_t* fullW = emptyP + SP;
+  uint64_t* emptyW = fullW + SW;
+  uint64_t* tfull = emptyW + SW;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SP; ++i) {
+      mbar_init(&fullP[i], 1);
+      mbar_init(&emptyP[i], 1);
+    }
+    for (int i = 0; i < SW; ++i) {
+      mbar_init(&fullW[i], 1);
+      mbar_init(&emptyW[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- row-parity patch producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int mt = tile;
+        const int w0 = (mt % p.tiles_w) * kTrW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * (2 * kTrI);
+        const int n0 = mt / p.tiles_h;
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          for (int par = 0; par < 2; ++par) {  // even rows h0 + 2k, then odd rows h0 - 1 + 2k  (k = 0..32)
+            mbar_wait(&emptyP[stage], phase ^ 1);
+            mbar_expect_tx(&fullP[stage], kTrPatchBytes);
+            tma_load_5d(sP + stage * kTrPatchStride, &tmX, &fullP[stage], chunk * 64, w0 - 1, par, h0 / 2 - par, n0);
+            if (++stage == SP) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------- weight producer: [tap of shift 0 | tap of shift 1] per view -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      const int oob = 9 * p.cin_pad;  // a box that starts past the last column is all zeros
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          for (int v = 0; v < 12; ++v) {
+            const int par = v / 6, r = (v % 6) / 3, dc = v % 3;
+            const int dr = par == 0 ? 2 * r : 2 * r - 1;             // view row offset: 0, 2 | -1, 1
+            const int tap_a = dr <= 1 ? (dr + 1) * 3 + dc : -1;      // shift 0 uses tap (dr, dc)
+            const int tap_b = dr >= 0 ? dr * 3 + dc : -1;            // shift 1 uses tap (dr - 1, dc)
+            const int col_a = tap_a >= 0 ? tap_a * p.cin_pad + chunk * 64 : oob;
+            const int col_b = tap_b >= 0 ? tap_b * p.cin_pad + chunk * 64 : oob;
+            mbar_wait(&emptyW[stage], phase ^ 1);
+            mbar_expect_tx(&fullW[stage], kTrWBytes);
+            tma_load_2d(sW + stage * kTrWBytes, &tmW, &fullW[stage], col_a, 0);
+            tma_load_2d(sW + stage * kTrWBytes + kTrWBytes / 2, &tmW, &fullW[stage], col_b, 0);
+            if (++stage == SW) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    constexpr uint32_t idesc0 = idesc_bf16_f32(128, 0, false, false);
+    constexpr uint32_t w_hi = desc_hi_sw128(1024), x_hi = desc_hi_sw128(kTrPitch * 128);
+    const uint32_t w_lo0 = desc_lo(smem_u32(sW), 16), x_lo0 = desc_lo(smem_u32(sP), 16);
+    int sp = 0, sw = 0;
+    uint32_t pp = 0, pw = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * (2 * kTrI);
+      const uint32_t idesc = idesc0 | (static_cast<uint32_t>(tr_cols(p.H, h0) >> 3) << 17);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 256;
+      for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+        for (int par = 0; par < 2; ++par) {
+          mbar_wait(&fullP[sp], pp);
+          const uint32_t x_st = x_lo0 + sp * (kTrPatchStride >> 4);
+          for (int v = 0; v < 6; ++v) {
+            const int r = v / 3, dc = v - r * 3;
+            mbar_wait(&fullW[sw], pw);
+            tc_fence_after();
+            const uint32_t w_lo = w_lo0 + sw * (kTrWBytes >> 4);
+            const uint32_t x_lo = x_st + (r * kTrPitch + dc) * 8;  // view start: patch row r, column dc (16-byte units)
+            const uint32_t first = (chunk | par | v) != 0 ? 1u : 0u;
+            if (elect_one()) {
+              umma_bf16_lohi(d, w_lo, w_hi, x_lo, x_hi, idesc, first);
+              umma_bf16_lohi(d, w_lo + 2, w_hi, x_lo + 2, x_hi, idesc, 1u);
+              umma_bf16_lohi(d, w_lo + 4, w_hi, x_lo + 4, x_hi, idesc, 1u);
+              umma_bf16_lohi(d, w_lo + 6, w_hi, x_lo + 6, x_hi, idesc, 1u);
+              umma_commit(&emptyW[sw]);
+            }
+            __syncwarp();
+            if (++sw == SW) {
+              sw = 0;
+              pw ^= 1;
+            }
+          }
+          if (elect_one()) umma_commit(&emptyP[sp]);
+          __syncwarp();
+          if (++sp == SP) {
+            sp = 0;
+            pp ^= 1;
+          }
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // --------------------------------- epilogue -----------------------------------
+    // TMEM lane = (shift, channel): warp quadrant wq = warp % 4 reads lanes 32 wq .. 32 wq + 31; warps 4-7 take accumulator
+    // columns [0, 128), warps 8-11 [128, 256). Column q = pixel (row pair q / 8, column q % 8) of the tile. A block of 32
+    // channels x 32 pixels is turned around through 2 KB of shared memory (2-byte stores, one 64-byte row per pixel) so
+    // that global memory sees 16-byte stores; a warp is a serial instruction stream, and at 2-byte global stores with
+    // per-element addressing the epilogue (~20 instructions per element) ran 2x longer than the tile's MMAs (ncu).
+    const int wq = warp & 3, chalf = (warp - 4) >> 2;
+    const int shift = wq >> 1, co = (wq & 1) * 32 + lane;
+    const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+    const bool want_stats = p.stat_partials != nullptr;
+    const bool affine = p.scale != nullptr, relu = p.relu != 0;
+    uint8_t* tbuf = sT + (warp - 4) * 2048;
+    const uint32_t tb_st = smem_u32(tbuf) + lane * 2;                       // + pixel * 64
+    const uint32_t tb_ld = smem_u32(tbuf) + (lane >> 2) * 64 + (lane & 3) * 16;  // + 8-pixel group * 512
+    const int jj = lane >> 2, part = lane & 3;  // this lane's pixel column / 8-channel group in the 16-byte phase
+    float S = 0.f, Q = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int mt = tile;
+      const int w0 = (mt % p.tiles_w) * kTrW;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * (2 * kTrI);
+      const int n = mt / p.tiles_h;
+      const int ncols = tr_cols(p.H, h0);
+      const int wvalid = p.W - w0;                       // columns j < wvalid are inside the image
+      const int ivalid = (p.H - h0 - shift + 1) >> 1;    // row pairs i < ivalid have row 2i + shift inside the image
+      __nv_bfloat16* gbase = p.y + n * p.ysn + (h0 + shift) * p.ysh + (w0 + jj) * p.ysw + (wq & 1) * 32 + part * 8;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        const int c0 = chalf * 128 + b * 32;
+        if (c0 >= ncols) break;
+        const int i0 = c0 >> 3;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * 256 + c0, r);
+        tmem_ld_wait();
+        if (want_stats) {
+          if (wvalid >= kTrW && i0 + 4 <= ivalid) {  // block entirely inside the image
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float v = __uint_as_float(r[t]);
+              S += v;
+              Q = fmaf(v, v, Q);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float v = (i0 + (t >> 3) < ivalid && (t & 7) < wvalid) ? __uint_as_float(r[t]) : 0.f;
+              S += v;
+              Q = fmaf(v, v, Q);
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float v = __uint_as_float(r[t]);
+          if (affine) {
+            v = fmaf(v, sc, sh);
+            if (relu) v = fmaxf(v, 0.f);
+          }
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(tb_st + t * 64), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        }
+        __syncwarp();
+        if (!(p.debug & 1) && jj < wvalid) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(tb_ld + k * 512) : "memory");
+            if (i0 + k < ivalid) *reinterpret_cast<uint4*>(gbase + 2 * (i0 + k) * p.ysh) = o;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    s_stats[(warp - 4) * 64 + lane] = S;
+    s_stats[(warp - 4) * 64 + 32 + lane] = Q;
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (p.stat_partials && threadIdx.x < 128) {
+    // channel c is held by the warps with (wq & 1) == c / 32: both shifts, both column halves
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63, half = c >> 5, l = c & 31;
+    float a = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+      for (int sft = 0; sft < 2; ++sft) a += s_stats[(ch * 4 + sft * 2 + half) * 64 + which * 32 + l];
+    p.stat_partials[static_cast<long long>(blockIdx.x) * 2 * p.cout_pad + which * p.cout_pad + c] = a;
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Pixel tile (TW x TH x TN <= 128) that wastes the fewest MMA rows for this image size.
 static void pick_tile(int N, int H, int W, int* TW, int* TH, int* TN) {
   double best = -1.0;
@@ -684,6 +1228,31 @@ static int launch_fprop_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return CVB_OK;
 }
 
+template <int BN>
+static int launch_fprop_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t st) {
+  using Cfg = Halo2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(conv_fprop_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  conv_fprop_halo2_kernel<BN><<<sm_count() & ~1, kHaloThreads, Cfg::kSmem, st>>>(tmA, tmB, p);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+static int launch_fprop_tr64(const CUtensorMap& tmX, const CUtensorMap& tmW, const FpropParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(conv_fprop_tr64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
+    configured = true;
+  }
+  const int grid = sm_count();  // every CTA writes its row of the BatchNorm partials (zeros when it has no tile)
+  conv_fprop_tr64_kernel<<<grid, kTrThreads, kTrSmem, st>>>(tmX, tmW, p);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -740,6 +1309,27 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   }
   CUtensorMap tmA, tmB;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int tr_mode = -1;  // CVB_TR64=0 keeps the pixel-major halo kernel for cout = 64 (A/B measurements)
+  if (tr_mode < 0) {
+    const char* e = getenv("CVB_TR64");
+    tr_mode = e ? atoi(e) : 1;
+  }
+  if (taps == 9 && y.c == 64 && (x.h % 2) == 0 && x.w >= kTrW && tr_mode != 0) {
+    // cout = 64: transposed kernel (weights on M, 256 pixels on N)
+    p.TW = kTrW; p.TH = 2 * kTrI; p.TN = 1;
+    p.tiles_w = (x.w + kTrW - 1) / kTrW;
+    p.tiles_h = (x.h + 2 * kTrI - 1) / (2 * kTrI);
+    p.tiles_n = x.n;
+    p.n_tiles = 1;
+    long long tr_total = 1LL * p.tiles_w * p.tiles_h * p.tiles_n;
+    CVB_REQUIRE(tr_total < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_fprop: too many tiles");
+    p.total_tiles = static_cast<int>(tr_total);
+    rc = make_act_tmap_rowpairs(&tmA, x, kTrW + 2, kTrI + 1);
+    if (rc) return rc;
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, 64);
+    if (rc) return rc;
+    return launch_fprop_tr64(tmA, tmB, p, st);
+  }
   if (taps == 9 && y.c <= 128 && x.w >= kHaloW && x.h >= 16) {
     // wide-and-shallow layer: halo kernel (one patch fetch per chunk, nine shifted descriptor views)
     p.TW = kHaloW; p.TH = kHaloH; p.TN = 1;
@@ -750,8 +1340,14 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     rc = make_act_tmap(&tmA, x, kHaloW + 2, kHaloH + 2, 1);
     if (rc) return rc;
-    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, y.c);
+    // CVB_HALO_PAIR=1 selects the CTA-pair kernel: correct, but measured ~2x SLOWER than the single-CTA kernel on
+    // B200, so it is off by default; read per call so that a test can exercise it.
+    const char* pe = getenv("CVB_HALO_PAIR");
+    const int pair_mode = pe ? atoi(pe) : 0;
+    const bool use_pair = pair_mode != 0 && p.total_tiles >= 2 && sm_count() >= 2 && (sm_count() & 1) == 0;
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, use_pair ? y.c / 2 : y.c);
     if (rc) return rc;
+    if (use_pair) return y.c == 64 ? launch_fprop_halo2<64>(tmA, tmB, p, st) : launch_fprop_halo2<128>(tmA, tmB, p, st);
     return y.c == 64 ? launch_fprop_halo<64>(tmA, tmB, p, st) : launch_fprop_halo<128>(tmA, tmB, p, st);
   }
   rc = make_act_tmap(&tmA, x, p.TW, p.TH, p.TN);

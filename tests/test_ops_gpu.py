@@ -60,6 +60,9 @@ CONV_CASES = [
     (1, 70, 9, 256, 64),
     (3, 17, 8, 64, 128),
     (1, 96, 40, 192, 128),
+    # CTA-pair halo kernel: more tile pairs than SM pairs (several accumulator phases), odd tile count
+    (8, 128, 100, 64, 64),
+    (5, 96, 88, 128, 128),
 ]
 
 
