@@ -273,6 +273,183 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-shift variant for cout_pad == 64. An MMA pays for every operand row it reads from shared memory, so N = 64 leaves
+// the tensor pipe half idle (ncu: 50 % active on these layers). Here the ROW offsets of the taps move to the dy operand:
+//   dW[co][ci][(dr, dc)] = sum_q  x[q + (0, dc)][ci] * dy[q - (dr, 0)][co]
+// A = the x patch (16 rows x 10 pixels, column halo only) viewed at column offset dc, two views per M = 128;
+// B = the dy patch (18 rows x 8 pixels, row halo, zero-filled by TMA outside the image) as N = 192 = three 64-wide atoms,
+// atom j = the patch shifted down by j rows = tap row dr = 1 - j. Two MMAs per K slice (views {dc0, dc1} and {dc1, dc2};
+// the duplicated dc1 rows are dropped by the epilogue) replace five N = 64 MMAs. One work item = one 64-channel ci chunk;
+// stream-K partition, workspace layout and the reduction kernels are those of the kernel above.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRsXRows = kWTileH * kWPitch;          // 160
+constexpr int kRsXBytes = kRsXRows * 128;            // 20480
+constexpr int kRsDRows = (kWTileH + 2) * kWTileW;    // 144
+constexpr int kRsDBytes = kRsDRows * 128;            // 18432
+constexpr int kRsStageBytes = kRsXBytes + kRsDBytes; // 38912
+constexpr int kRsStages = 5;
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv_wgrad_rs64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int S = kRsStages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * kRsStageBytes);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const long long u_begin = sk_begin(p.total_units, p.grid, blockIdx.x);
+  const long long u_end = sk_begin(p.total_units, p.grid, blockIdx.x + 1);
+  const int item_first = static_cast<int>(u_begin / p.total_tiles);
+  const int item_last = u_end > u_begin ? static_cast<int>((u_end - 1) / p.total_tiles) : item_first - 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item_first; item <= item_last; ++item) {
+        const long long base = 1LL * item * p.total_tiles;
+        const int tile_begin = static_cast<int>(max(u_begin, base) - base);
+        const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          int t = tile;
+          const int w0 = (t % p.tiles_w) * kWTileW;
+          t /= p.tiles_w;
+          const int h0 = (t % p.tiles_h) * kWTileH;
+          const int n0 = t / p.tiles_h;
+          uint8_t* sX = smem + stage * kRsStageBytes;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kRsStageBytes);
+          tma_load_4d(sX, &tmX, &full[stage], item * 64, w0 - 1, h0, n0);
+          tma_load_4d(sX + kRsXBytes, &tmDY, &full[stage], 0, w0, h0 - 1, n0);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    constexpr uint32_t idesc = idesc_bf16_f32(128, 192, true, true);
+    constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive rows of the x patch
+    constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy patch rows are dense
+    // LBO: A atoms = neighbouring column views (one pixel = 128 B apart); B atoms = the patch one row (8 pixels) further down
+    const uint32_t x_lo0 = desc_lo(smem_u32(smem), 128);
+    const uint32_t d_lo0 = desc_lo(smem_u32(smem) + kRsXBytes, kWTileW * 128);
+    constexpr uint32_t stage_lo = kRsStageBytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int seg = 0;
+    for (int item = item_first; item <= item_last; ++item, ++seg) {
+      const long long base = 1LL * item * p.total_tiles;
+      const int tile_begin = static_cast<int>(max(u_begin, base) - base);
+      const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
+      mbar_wait(tempty, (seg & 1) ^ 1);
+      tc_fence_after();
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kWTileH;
+        const int rows = min(kWTileH, p.H - h0);
+        const int slices = (rows + 1) >> 1;
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_lo = x_lo0 + stage * stage_lo, d_lo = d_lo0 + stage * stage_lo;
+        const uint32_t first = tile != tile_begin ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll 1
+          for (int s = 0; s < slices; ++s) {
+            const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
+            const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
+            umma_bf16_lohi(tmem_base, xs, a_hi, ds, b_hi, idesc, accum);            // column views dc = 0, 1
+            umma_bf16_lohi(tmem_base + 192, xs + 8, a_hi, ds, b_hi, idesc, accum);  // column views dc = 1, 2
+          }
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // --------------------------------- epilogue (once per item segment) -----------------------------------
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int atom = row >> 6, r = row & 63;
+    int seg = 0;
+    for (int item = item_first; item <= item_last; ++item, ++seg) {
+      const int part = static_cast<int>(blockIdx.x) - sk_owner(p.total_units, p.grid, 1LL * item * p.total_tiles);
+      const int ci = item * 64 + r;
+      mbar_wait(tfull, seg & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const int dc = a + atom;             // accumulator 0: views (0, 1); accumulator 1: views (1, 2)
+        const bool keep = !(a == 1 && atom == 0);  // view 1 was already taken from accumulator 0
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+          const int tap = (2 - j) * 3 + dc;  // atom j of N = tap row dr = 1 - j
+          float* dst = p.ws + ((static_cast<long long>(part) * p.taps + tap) * p.cin_pad + ci) * p.cout_pad;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + a * 192 + j * 64 + c0, v);
+            tmem_ld_wait();
+            if (keep) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(dst + c0 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Part reduction, phase 1: slot 0 += slots 1 .. parts-1 of the item an element belongs to (16-byte accesses; the item and
 // its part count follow from the element's position with the same integer arithmetic the main kernel uses).
 __global__ void __launch_bounds__(256) wgrad_partsum_kernel(float* __restrict__ ws, WgradParams p, int BN) {
@@ -340,6 +517,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 struct WgradPlan {
   WgradParams p;
   int BN;
+  bool rowshift;  // cout_pad == 64: conv_wgrad_rs64_kernel
   int grid;
   int smem;
   long long ws_bytes;
@@ -364,6 +542,32 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.cout_pad = dy.c;
   const int BN = (dy.c % 256 == 0) ? 256 : ((dy.c % 128 == 0) ? 128 : 64);
   plan->BN = BN;
+  // CVB_WGRAD_RS=0 keeps the N = 64 kernel for cout = 64 (A/B measurements); read per call
+  const char* rs_env = getenv("CVB_WGRAD_RS");
+  plan->rowshift = taps == 9 && dy.c == 64 && !(rs_env && atoi(rs_env) == 0);
+  if (plan->rowshift) {
+    p.CM = 1;
+    p.T = 9;
+    p.n_tap_groups = 1;
+    p.n_co_tiles = 1;
+    p.n_ci_tiles = x.c / 64;
+    p.stage_bytes = kRsStageBytes;
+    p.stages = kRsStages;
+    p.items = p.n_ci_tiles;
+    p.total_units = 1LL * p.items * p.total_tiles;
+    p.grid = static_cast<int>(p.total_units < sm_count() ? p.total_units : sm_count());
+    int slots_rs = 1;
+    for (int item = 0; item < p.items; ++item) {
+      const long long u0 = 1LL * item * p.total_tiles;
+      const int parts = sk_owner(p.total_units, p.grid, u0 + p.total_tiles - 1) - sk_owner(p.total_units, p.grid, u0) + 1;
+      if (parts > slots_rs) slots_rs = parts;
+    }
+    p.slots = slots_rs;
+    plan->grid = p.grid;
+    plan->smem = 1024 + kRsStages * kRsStageBytes + 256;
+    plan->ws_bytes = 1LL * slots_rs * taps * x.c * dy.c * 4;
+    return CVB_OK;
+  }
   p.CM = (x.c % 128 == 0) ? 2 : 1;
   // accumulators: accs * BN <= 512 TMEM columns, accs <= kMaxAccs; one accumulator = two 64-row atoms
   int max_accs = 512 / BN;
@@ -437,17 +641,32 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, CVB_ERR_INVALID_ARG, "conv_wgrad: workspace not 16-byte aligned");
   plan.p.ws = static_cast<float*>(workspace);
   CUtensorMap tmX, tmDY;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan.rowshift) {
+    rc = make_act_tmap(&tmX, x, kWTileW + 2, kWTileH, 1);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmDY, dy, kWTileW, kWTileH + 2, 1);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+      CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_rs64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kWgradSmemBudget));
+      configured = true;
+    }
+    conv_wgrad_rs64_kernel<<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
+    CVB_LAUNCH_CHECK();
+  } else {
   rc = make_act_tmap(&tmX, x, kWTileW + 2, kWTileH + 2, 1);
   if (rc) return rc;
   rc = make_act_tmap(&tmDY, dy, kWTileW, kWTileH, 1);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (plan.BN) {
     case 256: rc = launch_wgrad<256>(tmX, tmDY, plan, st); break;
     case 128: rc = launch_wgrad<128>(tmX, tmDY, plan, st); break;
     default: rc = launch_wgrad<64>(tmX, tmDY, plan, st); break;
   }
   if (rc) return rc;
+  }
   // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
   int bci = 32;
   while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((x.c + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;

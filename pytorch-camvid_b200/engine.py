@@ -566,11 +566,17 @@ def run_module(module, plan_cls, x):
     if x.shape[2] < 32 or x.shape[3] < 32:
         raise RuntimeError("input must be at least 32x32 (five 2x2 poolings)")
     x = x.detach().float().contiguous()
-    n, _, h, w = x.shape
+    n, h, w = int(x.shape[0]), int(x.shape[2]), int(x.shape[3])  # concrete even under torch.jit.trace
     key = (n, h, w, x.device.index)
     plans = module.__dict__.setdefault("_plans", {})
     plan = plans.get(key)
     if plan is None or any(b.conv.weight.device != x.device for b in plan.blocks[:1]):
-        plan = plan_cls(module, n, h, w, x.device)
+        # buffer allocation is not part of the traced computation (writer.add_graph traces the first forward)
+        tracing = torch._C._get_tracing_state()
+        torch._C._set_tracing_state(None)
+        try:
+            plan = plan_cls(module, n, h, w, x.device)
+        finally:
+            torch._C._set_tracing_state(tracing)
         plans[key] = plan
     return net_forward_op(x, plan.param_list(), plan.handle, bool(module.training))
