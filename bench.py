@@ -11,7 +11,7 @@ over NCCL in buckets on a side stream. Rank 0 prints ONE JSON line.
   value         images/s, whole job, inputs resident in HBM, CUDA-event time over exactly K steps, max over ranks
   e2e           the same through the public API with HOST inputs: per step a pinned host->device copy of the fp32 NCHW
                 images + int64 masks and a device->host read of the loss
-  roofline      the dominant kernel (conv_fprop_kernel: every forward conv and every data-gradient conv):
+  roofline      the dominant kernel family (cvb_conv3x3_fprop: every forward conv and every data-gradient conv):
                 algorithmic FLOPs of its launches / their CUDA-event durations, measured on K further steps of the same
                 workload with an event pair around every C-ABI call (kept out of `value` so the events cannot perturb it)
   kernels       the same arithmetic for every other kernel family (HBM-bound ones in GB/s)
@@ -362,7 +362,7 @@ def run_b200(args):
                              "avg_us": round(sec / n * 1e6, 2), "share_of_step": round(sec / ksteps / step_s, 4)}
         top = kernels.get("conv3x3_fprop")
         if top:
-            roofline = {"kernel": "conv_fprop_kernel<BN> (forward + data-gradient convs)", "bound": "tensor",
+            roofline = {"kernel": "conv3x3 forward + data-gradient family (conv_fprop_kernel<256>, conv_fprop_halo_kernel<128>, conv_fprop_tr64_kernel)", "bound": "tensor",
                         "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s", "frac": top["frac"],
                         "peak_source": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                         "frac_of_burst_peak": round(top["achieved"] / pk["tf_burst"], 4),

@@ -94,47 +94,54 @@ static int reduce_launch_cfg(const cvb_view& v, int rows, int* grid) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finalize kernels: a block owns 32 channels; its 16 warps split the partial rows (coalesced 128-byte row reads),
-// accumulate in double and combine through 4 KB of shared memory (one quantity at a time: like the reduce kernel they
-// must fit next to a resident weight-gradient CTA), then warp 0 finishes the 32 channels.
+// finalize kernels: tiny and latency-bound, and they sit on the critical path twice per block (forward statistics,
+// backward coefficients). A block owns 8 channels; a warp load covers 4 partial rows x 8 channels (four 32-byte
+// sectors), 16 warps stride over the rows with 4 loads of each quantity in flight, so the dependent-load chain is
+// rows / 256 deep instead of rows / 64. Combine: shuffles over the 4 row lanes, then 2 KB of shared memory (the kernels
+// must fit next to a resident weight-gradient CTA, see bn_reduce_kernel). Lanes 0-7 of warp 0 finish the 8 channels.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kFinThreads = 512;
 constexpr int kFinWarps = kFinThreads / 32;
+constexpr int kFinCh = 8;  // channels per block
 
 __device__ __forceinline__ void reduce_partial_rows(const float* __restrict__ partials, int rows, int pstride, int ch,
                                                     bool ch_ok, double* s1_out, double* s2_out) {
-  __shared__ double sh[kFinWarps][32];
+  __shared__ double sh[2][kFinWarps][kFinCh];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int rsub = lane >> 3;  // which of the 4 rows of a warp load
   double s1 = 0.0, s2 = 0.0;
   if (ch_ok) {
-    int r = wq;
-    for (; r + 3 * kFinWarps < rows; r += 4 * kFinWarps) {  // 8 independent loads in flight per thread
+    constexpr int RS = kFinWarps * 4;  // rows covered by one load of every warp
+    int r = wq * 4 + rsub;
+    for (; r + 3 * RS < rows; r += 4 * RS) {
       float a0 = partials[(2LL * r) * pstride + ch], b0 = partials[(2LL * r + 1) * pstride + ch];
-      float a1 = partials[(2LL * (r + kFinWarps)) * pstride + ch], b1 = partials[(2LL * (r + kFinWarps) + 1) * pstride + ch];
-      float a2 = partials[(2LL * (r + 2 * kFinWarps)) * pstride + ch], b2 = partials[(2LL * (r + 2 * kFinWarps) + 1) * pstride + ch];
-      float a3 = partials[(2LL * (r + 3 * kFinWarps)) * pstride + ch], b3 = partials[(2LL * (r + 3 * kFinWarps) + 1) * pstride + ch];
+      float a1 = partials[(2LL * (r + RS)) * pstride + ch], b1 = partials[(2LL * (r + RS) + 1) * pstride + ch];
+      float a2 = partials[(2LL * (r + 2 * RS)) * pstride + ch], b2 = partials[(2LL * (r + 2 * RS) + 1) * pstride + ch];
+      float a3 = partials[(2LL * (r + 3 * RS)) * pstride + ch], b3 = partials[(2LL * (r + 3 * RS) + 1) * pstride + ch];
       s1 += (static_cast<double>(a0) + a1) + (static_cast<double>(a2) + a3);
       s2 += (static_cast<double>(b0) + b1) + (static_cast<double>(b2) + b3);
     }
-    for (; r < rows; r += kFinWarps) {
+    for (; r < rows; r += RS) {
       s1 += static_cast<double>(partials[(2LL * r) * pstride + ch]);
       s2 += static_cast<double>(partials[(2LL * r + 1) * pstride + ch]);
     }
   }
-  sh[wq][lane] = s1;
-  __syncthreads();
-  if (wq == 0) {
-    s1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < kFinWarps; ++q) s1 += sh[q][lane];
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  if (lane < kFinCh) {
+    sh[0][wq][lane] = s1;
+    sh[1][wq][lane] = s2;
   }
   __syncthreads();
-  sh[wq][lane] = s2;
-  __syncthreads();
-  if (wq == 0) {
-    s2 = 0.0;
+  if (threadIdx.x < kFinCh) {
+    s1 = s2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < kFinWarps; ++q) s2 += sh[q][lane];
+    for (int q = 0; q < kFinWarps; ++q) {
+      s1 += sh[0][q][lane];
+      s2 += sh[1][q][lane];
+    }
   }
   *s1_out = s1;
   *s2_out = s2;
@@ -145,10 +152,10 @@ bn_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pa
                    double unbias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ conv_bias, float* running_mean, float* running_var, float momentum,
                    float eps, float* mean, float* invstd, float* scale, float* shift) {
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
   double s1, s2;
   reduce_partial_rows(partials, rows, pstride, ch, ch < c, &s1, &s2);
-  if (threadIdx.x >= 32 || ch >= c_pad) return;
+  if (threadIdx.x >= kFinCh || ch >= c_pad) return;
   if (ch >= c) {
     scale[ch] = 0.f;
     shift[ch] = 0.f;
@@ -176,10 +183,10 @@ __global__ void __launch_bounds__(kFinThreads)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int c_pad, int pstride, double inv_count,
                        const float* __restrict__ gamma, const float* __restrict__ mean,
                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
   double sg, sgy;
   reduce_partial_rows(partials, rows, pstride, ch, ch < c, &sg, &sgy);
-  if (threadIdx.x >= 32 || ch >= c_pad) return;
+  if (threadIdx.x >= kFinCh || ch >= c_pad) return;
   if (ch >= c) {
     coef[ch] = 0.f;
     coef[c_pad + ch] = 0.f;
@@ -344,7 +351,7 @@ extern "C" int cvb_bn_finalize(const float* partials, int rows, int c, int c_pad
               "bn_finalize: running_mean and running_var must both be given or both be NULL");
   double inv = 1.0 / static_cast<double>(count);
   double unbias = count > 1 ? static_cast<double>(count) / static_cast<double>(count - 1) : 1.0;
-  bn_finalize_kernel<<<(c_pad + 31) / 32, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(c_pad + kFinCh - 1) / kFinCh, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, c, c_pad, c_pad, inv, unbias, gamma, beta, conv_bias, running_mean, running_var, momentum, eps,
       mean, invstd, scale, shift);
   CVB_LAUNCH_CHECK();
@@ -357,7 +364,7 @@ extern "C" int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c
   CVB_REQUIRE(partials && gamma && mean && invstd && dgamma && dbeta && coef, CVB_ERR_INVALID_ARG,
               "bn_bwd_finalize: null pointer");
   CVB_REQUIRE(rows > 0 && c > 0 && c_pad >= c && count > 0, CVB_ERR_INVALID_ARG, "bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<(c_pad + 31) / 32, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_bwd_finalize_kernel<<<(c_pad + kFinCh - 1) / kFinCh, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, c, c_pad, c_pad, 1.0 / static_cast<double>(count), gamma, mean, invstd, dgamma, dbeta, coef);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

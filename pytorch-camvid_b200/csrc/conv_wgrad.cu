@@ -39,6 +39,7 @@ constexpr int kMaxAccs = 8;
 struct WgradParams {
   int N, H, W;
   int tiles_w, tiles_h, total_tiles;
+  int th;    // pixel-tile height (even, <= kWTileH): 16 unless a shorter tile wastes much less of a small image
   int taps;  // 9 or 1
   int cin_pad, cout_pad;
   int CM, T;  // 64-channel ci chunks per M=128 accumulator (1 or 2), taps per work item
@@ -124,7 +125,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // ------------------------------- TMA producer -------------------------------
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.CM) * kWPatchBytes + b_units * kWDyBytes;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.CM) * (p.th + 2) * kWPitch * 128 + b_units * p.th * kWTileW * 128;
       for (int item = item_first; item <= item_last; ++item) {
         const int co_tile = item % p.n_co_tiles;
         const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
@@ -135,7 +136,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           int t = tile;
           const int w0 = (t % p.tiles_w) * kWTileW;
           t /= p.tiles_w;
-          const int h0 = (t % p.tiles_h) * kWTileH;
+          const int h0 = (t % p.tiles_h) * p.th;
           const int n0 = t / p.tiles_h;
           uint8_t* sX = smem + stage * p.stage_bytes;
           uint8_t* sD = sX + p.CM * kWPatchStride;
@@ -186,8 +187,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait(tempty, (seg & 1) ^ 1);
       tc_fence_after();
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kWTileH;
-        const int rows = min(kWTileH, p.H - h0);
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
+        const int rows = min(p.th, p.H - h0);
         const int slices = (rows + 1) >> 1;  // K slices of two tile rows that touch the image
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -533,7 +534,19 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   memset(&p, 0, sizeof(p));
   p.N = x.n; p.H = x.h; p.W = x.w;
   p.tiles_w = (x.w + kWTileW - 1) / kWTileW;
-  p.tiles_h = (x.h + kWTileH - 1) / kWTileH;
+  p.th = kWTileH;
+  if (x.h < 2 * kWTileH && !(taps == 9 && dy.c == 64)) {
+    // small images (22 or 11 rows at the bottom of the networks): a 16-row tile would be up to a third padding
+    int best = (x.h + kWTileH - 1) / kWTileH * kWTileH;
+    for (int th = kWTileH - 2; th >= 8; th -= 2) {
+      const int cover = (x.h + th - 1) / th * th;
+      if (cover * 100 < best * 85) {
+        best = cover;
+        p.th = th;
+      }
+    }
+  }
+  p.tiles_h = (x.h + p.th - 1) / p.th;
   long long tiles = 1LL * p.tiles_w * p.tiles_h * x.n;
   CVB_REQUIRE(tiles < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_wgrad: too many pixel tiles");
   p.total_tiles = static_cast<int>(tiles);
@@ -656,9 +669,9 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
     conv_wgrad_rs64_kernel<<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
     CVB_LAUNCH_CHECK();
   } else {
-  rc = make_act_tmap(&tmX, x, kWTileW + 2, kWTileH + 2, 1);
+  rc = make_act_tmap(&tmX, x, kWTileW + 2, plan.p.th + 2, 1);
   if (rc) return rc;
-  rc = make_act_tmap(&tmDY, dy, kWTileW, kWTileH, 1);
+  rc = make_act_tmap(&tmDY, dy, kWTileW, plan.p.th, 1);
   if (rc) return rc;
   switch (plan.BN) {
     case 256: rc = launch_wgrad<256>(tmX, tmDY, plan, st); break;

@@ -17,30 +17,58 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_dynamic", "sm__cycles_active.avg"]
 
 
-def launches(path):
+FAMILIES = {"conv3x3_fprop": ("conv_fprop_kernel", "conv_fprop_halo_kernel", "conv_fprop_halo2_kernel", "conv_fprop_tr64_kernel"),
+            "conv3x3_wgrad": ("conv_wgrad_kernel", "conv_wgrad_rs64_kernel")}
+
+
+def launches(path, traffic_out=None):
+    """Summarises ONE training step of the launch list: the launches between the last two im2col3x3 kernels (one per
+    forward pass), so warm-up steps and the end-to-end loop of bench.py do not dilute the shares. With a second path:
+    also writes the per-launch DRAM traffic of the conv kernel families (bench.py's roofline.traffic)."""
     rows = list(csv.reader(open(path)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h = rows[hdr]
-    kn, mn, mv, mu = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
-    agg = collections.OrderedDict()
+    idc, kn, mn, mv, mu = h.index("ID"), h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    per = collections.OrderedDict()  # launch id -> dict
     for r in rows[hdr + 1:]:
         if len(r) <= mv:
             continue
-        name = re.sub(r"\(.*", "", r[kn])
+        d = per.setdefault(r[idc], {"name": re.sub(r"\(.*", "", r[kn]), "us": 0.0, "rd": 0.0, "wr": 0.0})
         v = float(r[mv].replace(",", ""))
-        a = agg.setdefault(name, {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
         if r[mn] == "gpu__time_duration.sum":
-            a["n"] += 1
-            a["us"] += v / 1e3 if r[mu] in ("ns", "nsecond") else (v * 1e3 if r[mu] in ("ms", "msecond") else v)
+            d["us"] = v / 1e3 if r[mu] in ("ns", "nsecond") else (v * 1e3 if r[mu] in ("ms", "msecond") else v)
         elif r[mn] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[mu], 1.0)
-            a["rd" if "read" in r[mn] else "wr"] += v * scale
+            d["rd" if "read" in r[mn] else "wr"] = v * scale
+    seq = list(per.values())
+    marks = [i for i, d in enumerate(seq) if "im2col3x3" in d["name"]]
+    if len(marks) >= 2:
+        seq = seq[marks[-2]:marks[-1]]
+    agg = collections.OrderedDict()
+    for d in seq:
+        a = agg.setdefault(d["name"], {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
+        a["n"] += 1
+        for k in ("us", "rd", "wr"):
+            a[k] += d[k]
     tot = sum(v["us"] for v in agg.values())
     n = sum(v["n"] for v in agg.values())
-    print(f"# ncu launch list: {n} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, serialised: compare shares)\n")
+    print(f"# ncu launch list of one training step: {n} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, "
+          f"serialised: compare shares)\n")
     print("| kernel | launches | total us | share | DRAM read MB | DRAM write MB |\n|---|---|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
         print(f"| `{k[:100]}` | {v['n']} | {v['us']:.1f} | {100 * v['us'] / tot:.1f}% | {v['rd'] / 1e6:.1f} | {v['wr'] / 1e6:.1f} |")
+    if traffic_out:
+        import json
+        out = {}
+        for fam, names in FAMILIES.items():
+            sel = [v for k, v in agg.items() if any(re.search(r"\b" + nm + r"\b", k) for nm in names)]
+            cnt = sum(v["n"] for v in sel)
+            if cnt:
+                out[fam] = {"launches": cnt, "dram_bytes_per_launch": sum(v["rd"] + v["wr"] for v in sel) / cnt,
+                            "share_of_step_ncu": round(sum(v["us"] for v in sel) / tot, 4),
+                            "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over "
+                                      f"the launches of one UNet 16x3x360x480 step ({path})"}
+        json.dump(out, open(traffic_out, "w"), indent=1)
     return agg
 
 
@@ -59,4 +87,4 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
