@@ -220,7 +220,7 @@ def run_b200(args):
     if world > 1:
         parallel.data_parallel(net)
     loss_fn = CrossEntropyLoss()
-    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0)
+    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0)  # as train.py:100 (fused=True: same speed)
 
     g = torch.Generator().manual_seed(1 + rank)
     nbuf = 2

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 1
+#define CVB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CVB_API __attribute__((visibility("default")))
@@ -103,6 +103,17 @@ typedef struct {
   const float* scale;
   const float* shift;
   int32_t relu;
+  /* data-gradient mode (ABI 2): the output of this call is da, the gradient w.r.t. the activation of the block that
+   * precedes it, and that block's BatchNorm+ReLU backward (aten::threshold_backward + native_batch_norm_backward,
+   * train.py:131) starts with a reduction over exactly this tensor. With bwd_partials != NULL the kernel emits it from
+   * its epilogue: per-CTA partial sums of g = da*[bwd_y*bwd_scale[c]+bwd_shift[c] > 0] and g*bwd_y over the valid pixels,
+   * fp32 [cvb_conv_stat_rows()][2][y.c], from the bf16-rounded da it stores -- what cvb_bn_relu_bwd_reduce would read
+   * back from memory. bwd_y = that block's raw conv output (same shape as y). Only honoured where
+   * cvb_conv3x3_fprop_fuses_bwd_stats() says so; mutually exclusive with stat_partials / scale. */
+  cvb_view bwd_y;
+  const float* bwd_scale;
+  const float* bwd_shift;
+  float* bwd_partials;
 } cvb_conv_epilogue;
 
 /* Rows of the stat_partials buffer the conv writes (== its grid size; depends only on the device). */
@@ -111,6 +122,9 @@ CVB_API int cvb_conv_stat_rows(void);
  * x.c must equal cin_pad (multiple of 64), y.c == cout_pad (multiple of 64). The same entry point computes the
  * data gradient when given dy as `x` and the cvb_pack_weights_dgrad matrix. */
 CVB_API int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_view y, const cvb_conv_epilogue* ep, void* stream);
+/* 1 if cvb_conv3x3_fprop on these views runs a kernel that implements the bwd_* epilogue (today: the transposed
+ * cout_pad = 64 kernel), 0 if the caller has to run cvb_bn_relu_bwd_reduce itself. Pure host query. */
+CVB_API int cvb_conv3x3_fprop_fuses_bwd_stats(cvb_view x, cvb_view y, int taps);
 
 /* Weight gradient (aten::convolution_backward weight grad): dw[co][ci][r][s] = sum_{n,h,w} dy[n,h,w,co] *
  * x[n,h+r-1,w+s-1,ci], written as OIHW fp32 [cout,cin,3,3] (taps==1: [cout, cin9] with x the im2col view).

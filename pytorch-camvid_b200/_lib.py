@@ -22,7 +22,8 @@ class View(ctypes.Structure):
 class ConvEpilogue(ctypes.Structure):
     """cvb_conv_epilogue."""
     _fields_ = [("stat_partials", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
-                ("relu", ctypes.c_int32)]
+                ("relu", ctypes.c_int32), ("bwd_y", View), ("bwd_scale", ctypes.c_void_p),
+                ("bwd_shift", ctypes.c_void_p), ("bwd_partials", ctypes.c_void_p)]
 
 
 _P = ctypes.c_void_p
@@ -44,6 +45,7 @@ SIGNATURES = {
     "cvb_pack_weights_batch": (_I, [_P, _I, _I, _I, _P]),
     "cvb_conv_stat_rows": (_I, []),
     "cvb_conv3x3_fprop": (_I, [View, _P, _I, View, ctypes.POINTER(ConvEpilogue), _P]),
+    "cvb_conv3x3_fprop_fuses_bwd_stats": (_I, [View, View, _I]),
     "cvb_conv3x3_wgrad_workspace_bytes": (_L, [View, View, _I]),
     "cvb_conv3x3_wgrad": (_I, [View, View, _I, _P, _I, _I, _P, _L, _P]),
     "cvb_bn_stats": (_I, [View, _P, _I, _P]),
@@ -95,7 +97,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.cvb_abi_version() != 1:
+    if lib.cvb_abi_version() != 2:
         raise RuntimeError("libcamvid_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -32,6 +32,12 @@ struct FpropParams {
   const float* scale;
   const float* shift;
   int relu;
+  // data-gradient mode: BatchNorm+ReLU backward statistics of the consuming block (cvb_conv_epilogue::bwd_*)
+  const __nv_bfloat16* by;
+  long long bysn, bysh, bysw;
+  const float* bscale;
+  const float* bshift;
+  float* bpartials;
   int debug;  // development knobs (CVB_DEBUG env): bit 0 = skip the output stores, bit 1 = MMA-thread wait trace
   long long* trace;  // with debug bit 1: the stat_partials buffer reinterpreted (statistics are then not produced)
 };
@@ -1077,6 +1083,16 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const uint32_t tb_ld = smem_u32(tbuf) + (lane >> 2) * 64 + (lane & 3) * 16;  // + 8-pixel group * 512
     const int jj = lane >> 2, part = lane & 3;  // this lane's pixel column / 8-channel group in the 16-byte phase
     float S = 0.f, Q = 0.f;
+    // BatchNorm+ReLU backward statistics of the consuming block, gathered in the 16-byte phase (a thread's 8 channels
+    // never change): g = da * [y * scale + shift > 0], sums of g and g * y
+    const bool bwd = p.bpartials != nullptr;
+    float bsc[8], bsh[8], BS[8], BQ[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bsc[j] = bwd ? __ldg(p.bscale + (wq & 1) * 32 + part * 8 + j) : 0.f;
+      bsh[j] = bwd ? __ldg(p.bshift + (wq & 1) * 32 + part * 8 + j) : 0.f;
+      BS[j] = BQ[j] = 0.f;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1090,6 +1106,19 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       const int wvalid = p.W - w0;                       // columns j < wvalid are inside the image
       const int ivalid = (p.H - h0 - shift + 1) >> 1;    // row pairs i < ivalid have row 2i + shift inside the image
       __nv_bfloat16* gbase = p.y + n * p.ysn + (h0 + shift) * p.ysh + (w0 + jj) * p.ysw + (wq & 1) * 32 + part * 8;
+      const __nv_bfloat16* ybase = p.by + n * p.bysn + (h0 + shift) * p.bysh + (w0 + jj) * p.bysw + (wq & 1) * 32 + part * 8;
+      // y of the consuming block for the backward statistics: its addresses do not depend on the accumulator, so block
+      // b + 1 is fetched while block b is processed (block 0 before the wait for the MMAs)
+      uint4 ynext[4];
+      auto fetch_y = [&](int blk, uint4 (&dst)[4]) {
+        const int ib = (chalf * 128 + blk * 32) >> 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dst[k] = (bwd && blk < 4 && jj < wvalid && ib + k < ivalid && chalf * 128 + blk * 32 < ncols)
+                       ? ldg16(ybase + 2 * (ib + k) * p.bysh)
+                       : make_uint4(0u, 0u, 0u, 0u);
+      };
+      fetch_y(0, ynext);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -1097,6 +1126,10 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int c0 = chalf * 128 + b * 32;
         if (c0 >= ncols) break;
         const int i0 = c0 >> 3;
+        uint4 ycur[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ycur[k] = ynext[k];
+        fetch_y(b + 1, ynext);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * 256 + c0, r);
         tmem_ld_wait();
@@ -1133,7 +1166,20 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           for (int k = 0; k < 4; ++k) {
             uint4 o;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(tb_ld + k * 512) : "memory");
-            if (i0 + k < ivalid) *reinterpret_cast<uint4*>(gbase + 2 * (i0 + k) * p.ysh) = o;
+            if (i0 + k < ivalid) {
+              *reinterpret_cast<uint4*>(gbase + 2 * (i0 + k) * p.ysh) = o;
+              if (bwd) {
+                float g[8], yv[8];
+                unpack8(o, g);
+                unpack8(ycur[k], yv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float gj = fmaf(yv[j], bsc[j], bsh[j]) > 0.f ? g[j] : 0.f;
+                  BS[j] += gj;
+                  BQ[j] = fmaf(gj, yv[j], BQ[j]);
+                }
+              }
+            }
           }
         }
         __syncwarp();
@@ -1142,14 +1188,34 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    s_stats[(warp - 4) * 64 + lane] = S;
-    s_stats[(warp - 4) * 64 + 32 + lane] = Q;
+    if (!bwd) {
+      s_stats[(warp - 4) * 64 + lane] = S;
+      s_stats[(warp - 4) * 64 + 32 + lane] = Q;
+    } else {
+      // lanes with the same 8-channel group differ in their pixel column (lane >> 2): fold them, lanes 0-3 write
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+          BS[j] += __shfl_xor_sync(0xffffffffu, BS[j], m);
+          BQ[j] += __shfl_xor_sync(0xffffffffu, BQ[j], m);
+        }
+      }
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s_stats[(warp - 4) * 64 + lane * 8 + j] = BS[j];
+          s_stats[(warp - 4) * 64 + 32 + lane * 8 + j] = BQ[j];
+        }
+      }
+    }
   }
 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (p.stat_partials && threadIdx.x < 128) {
+  float* partials_out = p.stat_partials ? p.stat_partials : p.bpartials;
+  if (partials_out && threadIdx.x < 128) {
     // channel c is held by the warps with (wq & 1) == c / 32: both shifts, both column halves
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63, half = c >> 5, l = c & 31;
     float a = 0.f;
@@ -1157,7 +1223,7 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
       for (int sft = 0; sft < 2; ++sft) a += s_stats[(ch * 4 + sft * 2 + half) * 64 + which * 32 + l];
-    p.stat_partials[static_cast<long long>(blockIdx.x) * 2 * p.cout_pad + which * p.cout_pad + c] = a;
+    partials_out[static_cast<long long>(blockIdx.x) * 2 * p.cout_pad + which * p.cout_pad + c] = a;
   }
   if (warp == 2) {
     tc_fence_after();
@@ -1253,6 +1319,16 @@ static int launch_fprop_tr64(const CUtensorMap& tmX, const CUtensorMap& tmW, con
   return CVB_OK;
 }
 
+// Kernel selection shared by the entry point and the cvb_conv3x3_fprop_fuses_bwd_stats query.
+static bool uses_tr64(const cvb_view& x, const cvb_view& y, int taps) {
+  static int tr_mode = -1;  // CVB_TR64=0 keeps the pixel-major halo kernel for cout = 64 (A/B measurements)
+  if (tr_mode < 0) {
+    const char* e = getenv("CVB_TR64");
+    tr_mode = e ? atoi(e) : 1;
+  }
+  return taps == 9 && y.c == 64 && (x.h % 2) == 0 && x.w >= kTrW && tr_mode != 0;
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -1309,12 +1385,21 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   }
   CUtensorMap tmA, tmB;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int tr_mode = -1;  // CVB_TR64=0 keeps the pixel-major halo kernel for cout = 64 (A/B measurements)
-  if (tr_mode < 0) {
-    const char* e = getenv("CVB_TR64");
-    tr_mode = e ? atoi(e) : 1;
+  const bool want_bwd = ep && ep->bwd_partials != nullptr;
+  if (want_bwd) {
+    CVB_REQUIRE(ep->bwd_scale && ep->bwd_shift && ep->bwd_y.ptr, CVB_ERR_INVALID_ARG, "conv_fprop: incomplete bwd_* epilogue");
+    CVB_REQUIRE(!ep->stat_partials && !ep->scale, CVB_ERR_INVALID_ARG,
+                "conv_fprop: the bwd_* epilogue excludes stat_partials and scale/shift");
+    rc = check_view(ep->bwd_y, "conv_fprop.bwd_y");
+    if (rc) return rc;
+    CVB_REQUIRE(same_shape(ep->bwd_y, y), CVB_ERR_INVALID_ARG, "conv_fprop: bwd_y and y shapes differ");
+    CVB_REQUIRE(uses_tr64(x, y, taps), CVB_ERR_UNSUPPORTED,
+                "conv_fprop: no kernel with the bwd_* epilogue for these views (ask cvb_conv3x3_fprop_fuses_bwd_stats)");
+    p.by = static_cast<const __nv_bfloat16*>(ep->bwd_y.ptr);
+    p.bysn = ep->bwd_y.sn; p.bysh = ep->bwd_y.sh; p.bysw = ep->bwd_y.sw;
+    p.bscale = ep->bwd_scale; p.bshift = ep->bwd_shift; p.bpartials = ep->bwd_partials;
   }
-  if (taps == 9 && y.c == 64 && (x.h % 2) == 0 && x.w >= kTrW && tr_mode != 0) {
+  if (uses_tr64(x, y, taps)) {
     // cout = 64: transposed kernel (weights on M, 256 pixels on N)
     p.TW = kTrW; p.TH = 2 * kTrI; p.TN = 1;
     p.tiles_w = (x.w + kTrW - 1) / kTrW;
@@ -1359,4 +1444,9 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     case 128: return launch_fprop<128>(tmA, tmB, p, st);
     default: return launch_fprop<64>(tmA, tmB, p, st);
   }
+}
+
+extern "C" int cvb_conv3x3_fprop_fuses_bwd_stats(cvb_view x, cvb_view y, int taps) {
+  if (x.n != y.n || x.h != y.h || x.w != y.w || (x.c % 64) != 0) return 0;
+  return uses_tr64(x, y, taps) ? 1 : 0;
 }

@@ -9,6 +9,7 @@ Reference topology: models/unet.py:35-156 and models/segnet.py:19-119; one "bloc
 BasicConv2d / BasicConv (conv3x3 pad 1 + BatchNorm2d + ReLU, models/unet.py:5-17, models/segnet.py:5-17).
 """
 import itertools
+import os
 import weakref
 from typing import List
 
@@ -23,6 +24,10 @@ from .ops import pad64
 # the wgrad MMAs overlap the memory-bound BatchNorm / pooling / upsampling passes. bench.py turns it off for its
 # per-kernel timing pass (one stream = unambiguous event brackets).
 OVERLAP_WGRAD = True
+# Data-gradient kernels CAN emit the BatchNorm+ReLU backward statistics of the block they feed (cvb_conv_epilogue.bwd_*).
+# Off by default: measured 1 % slower end to end -- the reduce pass it removes was already hidden under the side-stream
+# weight gradient, while the heavier epilogue lengthens the data gradient on the critical path (CVB_FUSE_BWD=1 enables).
+FUSE_BWD_STATS = os.environ.get("CVB_FUSE_BWD", "0") != "0"
 
 
 class Block:
@@ -54,6 +59,7 @@ class Block:
         self.c_ratio = self.cout / self.ce
         # offsets into the flat gradient buffer, assigned by the plan
         self.g_w = self.g_b = self.g_gamma = self.g_beta = None
+        self._fuses = None  # whether this block's data gradient emits its consumer's backward statistics (lazy)
 
     # ---- parameters in reference order: conv.weight, conv.bias, bn.weight, bn.bias
     def params(self):
@@ -113,28 +119,43 @@ class Block:
         ops.conv3x3(self.x, self.wf, self.a, taps=self.taps, scale=self._fold[0], shift=self._fold[1], relu=True,
                     algo_flops=self.flops)
 
-    def backward(self, da, dx, flat):
-        """da: gradient w.r.t. self.a (same view geometry); dx: view receiving the gradient w.r.t. self.x or None."""
+    def backward(self, da, dx, flat, consumer=None, stats_ready=False):
+        """da: gradient w.r.t. self.a (same view geometry); dx: view receiving the gradient w.r.t. self.x or None.
+        consumer: the block whose activation IS self.x (dx is its `da`, nothing else accumulates into it): where the
+        data-gradient kernel can, it emits that block's BatchNorm+ReLU backward reduction from its epilogue. Returns True
+        if it did; the caller passes that as `stats_ready` to the consumer's backward, which then skips its reduce pass."""
         p, v = self.plan, self.vec
         parts = p.parts_view(self.ce)  # the reduce kernel lays its partial rows out with the view's channel count
         ops.WORK_SCALE = self.c_ratio
         if self.ce != self.cout_pad:
             da = da[..., :self.ce]
-        ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows)
+        rows = p.stat_rows
+        if not stats_ready:
+            ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows)
+            rows = p.reduce_rows
         dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
         dbeta = flat[self.g_beta:self.g_beta + self.cout]
-        ops.bn_bwd_finalize(parts, p.reduce_rows, self.cout, self.ce, self.count, self.bn.weight.detach(), v[0],
+        ops.bn_bwd_finalize(parts, rows, self.cout, self.ce, self.count, self.bn.weight.detach(), v[0],
                             v[1], dgamma, dbeta, self.coef)
         ops.bn_relu_bwd_apply(da, self.y_e, v[2], v[3], self.coef, self.y_e)  # y now holds dy
         ops.WORK_SCALE = 1.0
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
-        if self.g_b is not None:
-            flat[self.g_b:self.g_b + self.cout].zero_()  # conv bias feeds a batch-stat BatchNorm: gradient is exactly 0
+        # (conv bias feeds a batch-stat BatchNorm: its gradient is exactly 0 -- the flat buffer starts zeroed)
         if p.wstream is None:
             ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+        fused = False
         if dx is not None:
             self._pack_d()
-            ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops)
+            if consumer is not None and FUSE_BWD_STATS:
+                if self._fuses is None:
+                    self._fuses = (consumer.ce == consumer.cout_pad == dx.shape[3]
+                                   and ops.conv3x3_fuses_bwd_stats(self.y, dx))
+                fused = self._fuses
+            if fused:
+                ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops,
+                            bwd=(consumer.y_e, consumer.vec[2], consumer.vec[3], p.parts_view(consumer.ce)))
+            else:
+                ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops)
         if p.wstream is not None:
             # The side stream picks the weight gradient up AFTER the data gradient: started together the two tensor-bound
             # kernels only split the SMs between them (measured: same finish time as back to back) and the HBM-bound
@@ -145,6 +166,7 @@ class Block:
             p.wstream.wait_event(ready)
             with torch.cuda.stream(p.wstream):
                 ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+        return fused
 
 
 class Plan:
@@ -241,7 +263,7 @@ class Plan:
 
     def _begin_backward(self):
         """Flat fp32 gradient buffer of this pass; under data parallelism its ranges are all-reduced as they fill."""
-        flat = torch.empty(self.flat_size, device=self.device)
+        flat = torch.zeros(self.flat_size, device=self.device)  # one memset instead of a fill per conv-bias slice
         self.reducer = self.module.__dict__.get("_cvb_reducer")
         if self.reducer is not None:
             self.reducer.begin(flat)
@@ -363,17 +385,18 @@ class UNetPlan(Plan):
         flat = self._begin_backward()
         ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.b_out.ce])
         last = self.dec[-1]
-        self.b_out.backward(self.d_out_a, last["dm1"], flat)
+        ready = self.b_out.backward(self.d_out_a, last["dm1"], flat, consumer=last["b1"])
         self._done(self.b_out)
         for d in reversed(self.dec):
             l = d["level"]
-            d["b1"].backward(d["dm1"], d["dm0"], flat)
+            ready = d["b1"].backward(d["dm1"], d["dm0"], flat, consumer=d["b0"], stats_ready=ready)
             self._done(d["b1"])
-            d["b0"].backward(d["dm0"], self.dcat[l], flat)
+            d["b0"].backward(d["dm0"], self.dcat[l], flat, stats_ready=ready)  # dcat feeds two blocks: not fused
             self._done(d["b0"])
             d["bu"].backward(self.dcat[l][d["win"]], d["dup"], flat)
             self._done(d["bu"])
             ops.bilinear2x_bwd(d["dup"], d["dsrc"])
+            ready = False  # the next stage's dm1 comes out of the upsampling backward
         for l in range(4, -1, -1):
             b0, b1 = self.enc[l]
             if l == 4:
@@ -383,9 +406,9 @@ class UNetPlan(Plan):
                 da = self.dcat[l][..., ch:]
                 # encoder activation feeds both the skip (already in dcat) and the pool: add the pool path
                 ops.maxpool2x2_bwd(self.dpooled[l], da, x=b1.a, accumulate=True)
-            b1.backward(da, self.d_enc_mid[l], flat)
+            ready = b1.backward(da, self.d_enc_mid[l], flat, consumer=b0)
             self._done(b1)
-            b0.backward(self.d_enc_mid[l], self.dpooled[l - 1] if l > 0 else None, flat)
+            b0.backward(self.d_enc_mid[l], self.dpooled[l - 1] if l > 0 else None, flat, stats_ready=ready)
             self._done(b0)
         return self._end_backward(flat)
 
@@ -470,20 +493,24 @@ class SegNetPlan(Plan):
         ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.dstages[-1]["blocks"][-1].ce])
         for ds in reversed(self.dstages):
             bl = ds["blocks"]
+            ready = False
             for j in range(len(bl) - 1, -1, -1):
-                bl[j].backward(ds["dacts"][j], ds["dacts"][j - 1] if j > 0 else ds["dun"], flat)
+                ready = bl[j].backward(ds["dacts"][j], ds["dacts"][j - 1] if j > 0 else ds["dun"], flat,
+                                       consumer=bl[j - 1] if j > 0 else None, stats_ready=ready)
                 self._done(bl[j])
             ops.maxunpool2x2_bwd(ds["dun"], ds["code"], ds["dsrc"])
         for s in range(4, -1, -1):
             st = self.stages[s]
             bl = st["blocks"]
             ops.maxpool2x2_bwd(st["dpooled"], st["dacts"][-1], code=st["code"])
+            ready = False
             for j in range(len(bl) - 1, -1, -1):
                 if j > 0:
                     dx = st["dacts"][j - 1]
                 else:
                     dx = self.stages[s - 1]["dpooled"] if s > 0 else None
-                bl[j].backward(st["dacts"][j], dx, flat)
+                ready = bl[j].backward(st["dacts"][j], dx, flat, consumer=bl[j - 1] if j > 0 else None,
+                                       stats_ready=ready)
                 self._done(bl[j])
         return self._end_backward(flat)
 

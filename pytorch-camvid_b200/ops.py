@@ -159,12 +159,21 @@ def pack_weights_batch(table, max_cout_pad, max_cin_pad, nbytes):
           table.shape[0], max_cout_pad, max_cin_pad, _stream())
 
 
-def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False, algo_flops=None):
-    """y = conv(x, wpack). Optional epilogues: BN statistics partials (train) or folded scale/shift(+ReLU) (eval).
+def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, relu=False, algo_flops=None, bwd=None):
+    """y = conv(x, wpack). Optional epilogues: BN statistics partials (train), folded scale/shift(+ReLU) (eval), or --
+    for a data gradient, bwd = (y_prev, scale_prev, shift_prev, partials) -- the BatchNorm+ReLU backward reduction of
+    the block that consumes this gradient (only where conv3x3_fuses_bwd_stats(x, y) is True).
     algo_flops: FLOPs of the un-padded convolution (roofline accounting); default = the padded GEMM's."""
     ep = ConvEpilogue(stat_partials.data_ptr() if stat_partials is not None else None,
                       scale.data_ptr() if scale is not None else None,
-                      shift.data_ptr() if shift is not None else None, 1 if relu else 0)
+                      shift.data_ptr() if shift is not None else None, 1 if relu else 0,
+                      view(None), None, None, None)
+    if bwd is not None:
+        by, bscale, bshift, bparts = bwd
+        _f32(bparts, "conv3x3.bwd_partials")
+        if bparts.numel() < stat_rows() * 2 * y.shape[3]:
+            raise RuntimeError("conv3x3: bwd partials too small")
+        ep.bwd_y, ep.bwd_scale, ep.bwd_shift, ep.bwd_partials = view(by), bscale.data_ptr(), bshift.data_ptr(), bparts.data_ptr()
     if stat_partials is not None:
         _f32(stat_partials, "conv3x3.stat_partials")
         if stat_partials.numel() < stat_rows() * 2 * y.shape[3]:
@@ -175,6 +184,10 @@ def conv3x3(x, wpack, y, taps=9, stat_partials=None, scale=None, shift=None, rel
                                2.0 * (x.numel() + y.numel() + wpack.numel())), _lib.load().cvb_conv3x3_fprop, view(x), _ptr(wpack), taps,
           view(y), ctypes.byref(ep), _stream())
     return y
+
+
+def conv3x3_fuses_bwd_stats(x, y, taps=9):
+    return bool(_lib.load().cvb_conv3x3_fprop_fuses_bwd_stats(view(x), view(y), taps))
 
 
 def conv3x3_wgrad_workspace_bytes(x, dy, taps=9):

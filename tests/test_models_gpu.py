@@ -361,3 +361,24 @@ def test_custom_op_schema_and_eval_backward_guard(cvb, cuda):
     loss = cnn.CrossEntropyLoss()(net(x.to(cuda)), t.to(cuda))
     with pytest.raises(RuntimeError, match="eval-mode"):
         loss.backward()
+
+
+def test_fused_bn_backward_statistics_path(cvb, cuda):
+    """engine.FUSE_BWD_STATS (off by default: slower end to end) routes the BatchNorm backward reduction of 64-channel
+    blocks through the data-gradient epilogue (cvb_conv_epilogue.bwd_*). Same sums from the same stored tensors: the
+    parameter gradients must agree with the default path to accumulation-order noise."""
+    from camvid_b200 import engine
+    cutils, cnn = cvb
+    grads = []
+    for fuse in (False, True):
+        engine.FUSE_BWD_STATS = fuse
+        try:
+            torch.manual_seed(5)
+            net = cutils.get_model("segnet", 3, 12).to(cuda).train()
+            x, t = O.synth_batch(2, 64, 48, seed=13)
+            cnn.CrossEntropyLoss()(net(x.to(cuda)), t.to(cuda)).backward()
+            grads.append({k: p.grad.clone() for k, p in net.named_parameters()})
+        finally:
+            engine.FUSE_BWD_STATS = False
+    worst = max(rel_err(grads[1][k], grads[0][k]) for k in grads[0] if not _is_conv_bias(net, k))
+    assert worst < 2e-3, worst

@@ -125,6 +125,51 @@ def test_conv_dgrad(ops, cuda, n, h, w, cin, cout):
     assert rel_err(to_nchw_f32(dx), ref) < 4e-3
 
 
+
+def test_conv_cta_pair_kernel_matches_single_cta(ops, cuda, monkeypatch):
+    """conv_fprop_halo2_kernel (cta_group::2, off by default because it is slower on B200) stays bit-identical to the
+    single-CTA halo kernel: same MMAs, same accumulation order."""
+    n, h, w, cin, cout = 3, 50, 44, 128, 128
+    x = to_nhwc_bf16(_rand((n, cin, h, w), cuda, 41))
+    wp = ops.pack_weights_fprop(_rand((cout, cin, 3, 3), cuda, 42, scale=(cin * 9) ** -0.5), 9, cout, cin)
+    outs, stats = [], []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CVB_HALO_PAIR", mode)
+        y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+        parts = torch.full((ops.stat_rows(), 2, cout), float("nan"), device=cuda)
+        ops.conv3x3(x, wp, y, stat_partials=parts)
+        torch.cuda.synchronize()
+        outs.append(y)
+        stats.append(parts.sum(0))
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(stats[1], stats[0]) < 1e-5
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 40, 24, 64, 64), (1, 70, 20, 64, 128), (3, 128, 100, 64, 64)])
+def test_conv_dgrad_emits_consumer_bn_backward_statistics(ops, cuda, n, h, w, cin, cout):
+    """cvb_conv_epilogue.bwd_*: the data-gradient kernel reduces g = da*[y*scale+shift > 0] and g*y for the block that
+    consumes da; must equal cvb_bn_relu_bwd_reduce run on the stored da (aten::native_batch_norm_backward's sums)."""
+    wt = _rand((cout, cin, 3, 3), cuda, 31, scale=(cin * 9) ** -0.5)
+    dy = to_nhwc_bf16(_rand((n, cout, h, w), cuda, 32))
+    y_prev = to_nhwc_bf16(_rand((n, cin, h, w), cuda, 33))
+    scale = torch.rand(cin, device=cuda) + 0.5
+    shift = torch.randn(cin, device=cuda) * 0.3
+    wd = ops.pack_weights_dgrad(wt, cout, cin)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=cuda)
+    assert ops.conv3x3_fuses_bwd_stats(dy, dx)
+    parts = torch.full((ops.stat_rows(), 2, cin), float("nan"), device=cuda)
+    ops.conv3x3(dy, wd, dx, bwd=(y_prev, scale, shift, parts))
+    dx_plain = torch.empty_like(dx)
+    ops.conv3x3(dy, wd, dx_plain)
+    assert torch.equal(dx, dx_plain)
+    rows = 4 * ops.sm_count()
+    ref = torch.empty(rows, 2, cin, device=cuda)
+    ops.bn_relu_bwd_reduce(dx, y_prev, scale, shift, ref, rows)
+    got, want = parts.double().sum(0), ref.double().sum(0)
+    assert torch.isfinite(got).all()
+    assert rel_err(got[0], want[0]) < 1e-4 and rel_err(got[1], want[1]) < 1e-4
+
+
 WGRAD_CASES = [
     (2, 16, 24, 64, 64),
     (2, 23, 31, 128, 64),
