@@ -1231,6 +1231,262 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Transposed variant for cout_pad == 128 (the half-resolution stages and the data gradients that land on 128 channels).
+// Same idea as the cout = 64 kernel without the row-shift trick: the 128 output channels ARE the M dimension,
+// D^T[cout][pixel] = W_tap[cout][cin] * X_tap[pixel][cin]^T, nine taps = nine shifted views of one 10 x 34 pixel patch
+// (the halo kernel's patch), N = 256 pixels (8 w x 32 h) per MMA. Per unit of work an MMA now reads 128 + 256 operand
+// rows instead of 2 x (128 + 128): 1.3x fewer (the halo kernel ran at the operand-row bound, ~113 clk per N = 128 MMA).
+// Epilogue as in the cout = 64 kernel: a thread owns one channel lane (statistics = two scalars), blocks of 32 channels x
+// 32 pixels are turned through shared memory into 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kT8StagesP = 2, kT8StagesW = 7;
+constexpr int kT8WBytes = 128 * 128;  // [128 cout][64 cin]
+constexpr int kT8Smem = 1024 + kT8StagesP * kPatchStride + kT8StagesW * kT8WBytes + 8 * 2048 + 8 * 64 * 4 + 256;
+
+__device__ __forceinline__ int t8_cols(int H, int h0) {
+  int rows = min(kHaloH, H - h0);
+  rows = (rows + 1) & ~1;  // N must be a multiple of 16
+  return rows * kHaloW;
+}
+
+__global__ void __launch_bounds__(kTrThreads, 1)
+conv_fprop_tr128_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                        const FpropParams p) {
+  constexpr int SP = kT8StagesP, SW = kT8StagesW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem;
+  uint8_t* sW = sP + SP * kPatchStride;
+  uint8_t* sT = sW + SW * kT8WBytes;                                // [8 epilogue warps][32 pixels][32 channels] bf16
+  float* s_stats = reinterpret_cast<float*>(sT + 8 * 2048);         // [8 epilogue warps][sum | sumsq][32 lanes]
+  uint64_t* fullP = reinterpret_cast<uint64_t*>(s_stats + 8 * 64);
+  uint64_t* emptyP = fullP + SP;
+  uint64_t* fullW = emptyP + SP;
+  uint64_t* emptyW = fullW + SW;
+  uint64_t* tfull = emptyW + SW;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SP; ++i) {
+      mbar_init(&fullP[i], 1);
+      mbar_init(&emptyP[i], 1);
+    }
+    for (int i = 0; i < SW; ++i) {
+      mbar_init(&fullW[i], 1);
+      mbar_init(&emptyW[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- activation-patch producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int mt = tile;
+        const int w0 = (mt % p.tiles_w) * kHaloW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * kHaloH;
+        const int n0 = mt / p.tiles_h;
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          mbar_wait(&emptyP[stage], phase ^ 1);
+          mbar_expect_tx(&fullP[stage], kPatchBytes);
+          tma_load_4d(sP + stage * kPatchStride, &tmX, &fullP[stage], chunk * 64, w0 - 1, h0 - 1, n0);
+          if (++stage == SP) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------- weight producer: one [128 cout][64 cin] tile per (chunk, tap) -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyW[stage], phase ^ 1);
+            mbar_expect_tx(&fullW[stage], kT8WBytes);
+            tma_load_2d(sW + stage * kT8WBytes, &tmW, &fullW[stage], tap * p.cin_pad + chunk * 64, 0);
+            if (++stage == SW) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    constexpr uint32_t idesc0 = idesc_bf16_f32(128, 0, false, false);
+    constexpr uint32_t w_hi = desc_hi_sw128(1024), x_hi = desc_hi_sw128((kHaloW + 2) * 128);
+    const uint32_t w_lo0 = desc_lo(smem_u32(sW), 16), x_lo0 = desc_lo(smem_u32(sP), 16);
+    int sp = 0, sw = 0;
+    uint32_t pp = 0, pw = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * kHaloH;
+      const uint32_t idesc = idesc0 | (static_cast<uint32_t>(t8_cols(p.H, h0) >> 3) << 17);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 256;
+      for (int chunk = 0; chunk < p.cin_chunks; ++chunk) {
+        mbar_wait(&fullP[sp], pp);
+        const uint32_t x_st = x_lo0 + sp * (kPatchStride >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&fullW[sw], pw);
+          tc_fence_after();
+          const uint32_t w_lo = w_lo0 + sw * (kT8WBytes >> 4);
+          const int dr = tap / 3, ds = tap - dr * 3;
+          const uint32_t x_lo = x_st + (dr * (kHaloW + 2) + ds) * 8;
+          const uint32_t first = (chunk | tap) != 0 ? 1u : 0u;
+          if (elect_one()) {
+            umma_bf16_lohi(d, w_lo, w_hi, x_lo, x_hi, idesc, first);
+            umma_bf16_lohi(d, w_lo + 2, w_hi, x_lo + 2, x_hi, idesc, 1u);
+            umma_bf16_lohi(d, w_lo + 4, w_hi, x_lo + 4, x_hi, idesc, 1u);
+            umma_bf16_lohi(d, w_lo + 6, w_hi, x_lo + 6, x_hi, idesc, 1u);
+            umma_commit(&emptyW[sw]);
+          }
+          __syncwarp();
+          if (++sw == SW) {
+            sw = 0;
+            pw ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&emptyP[sp]);
+        __syncwarp();
+        if (++sp == SP) {
+          sp = 0;
+          pp ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // --------------------------------- epilogue -----------------------------------
+    // TMEM lane = output channel: warp quadrant wq = warp % 4 reads lanes 32 wq .. 32 wq + 31; warps 4-7 take accumulator
+    // columns [0, 128), warps 8-11 [128, 256). Column q = pixel (row q / 8, column q % 8) of the tile.
+    const int wq = warp & 3, chalf = (warp - 4) >> 2;
+    const int co = wq * 32 + lane;
+    const float sc = p.scale ? __ldg(p.scale + co) : 1.f, sh = p.scale ? __ldg(p.shift + co) : 0.f;
+    const bool want_stats = p.stat_partials != nullptr;
+    const bool affine = p.scale != nullptr, relu = p.relu != 0;
+    uint8_t* tbuf = sT + (warp - 4) * 2048;
+    const uint32_t tb_st = smem_u32(tbuf) + lane * 2;
+    const uint32_t tb_ld = smem_u32(tbuf) + (lane >> 2) * 64 + (lane & 3) * 16;
+    const int jj = lane >> 2, part = lane & 3;
+    float S = 0.f, Q = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int mt = tile;
+      const int w0 = (mt % p.tiles_w) * kHaloW;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * kHaloH;
+      const int n = mt / p.tiles_h;
+      const int ncols = t8_cols(p.H, h0);
+      const int wvalid = p.W - w0;   // columns j < wvalid are inside the image
+      const int rvalid = p.H - h0;   // tile rows r < rvalid are inside the image
+      __nv_bfloat16* gbase = p.y + n * p.ysn + h0 * p.ysh + (w0 + jj) * p.ysw + wq * 32 + part * 8;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        const int c0 = chalf * 128 + b * 32;
+        if (c0 >= ncols) break;
+        const int r0 = c0 >> 3;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * 256 + c0, r);
+        tmem_ld_wait();
+        if (want_stats) {
+          if (wvalid >= kHaloW && r0 + 4 <= rvalid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float v = __uint_as_float(r[t]);
+              S += v;
+              Q = fmaf(v, v, Q);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float v = (r0 + (t >> 3) < rvalid && (t & 7) < wvalid) ? __uint_as_float(r[t]) : 0.f;
+              S += v;
+              Q = fmaf(v, v, Q);
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float v = __uint_as_float(r[t]);
+          if (affine) {
+            v = fmaf(v, sc, sh);
+            if (relu) v = fmaxf(v, 0.f);
+          }
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(tb_st + t * 64), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        }
+        __syncwarp();
+        if (!(p.debug & 1) && jj < wvalid) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(tb_ld + k * 512) : "memory");
+            if (r0 + k < rvalid) *reinterpret_cast<uint4*>(gbase + (r0 + k) * p.ysh) = o;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    s_stats[(warp - 4) * 64 + lane] = S;
+    s_stats[(warp - 4) * 64 + 32 + lane] = Q;
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (p.stat_partials && threadIdx.x < 256) {
+    // channel c is held by quadrant c / 32 of both column halves
+    const int which = threadIdx.x >> 7, c = threadIdx.x & 127, q = c >> 5, l = c & 31;
+    const float a = s_stats[q * 64 + which * 32 + l] + s_stats[(4 + q) * 64 + which * 32 + l];
+    p.stat_partials[static_cast<long long>(blockIdx.x) * 2 * p.cout_pad + which * p.cout_pad + c] = a;
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Pixel tile (TW x TH x TN <= 128) that wastes the fewest MMA rows for this image size.
 static void pick_tile(int N, int H, int W, int* TW, int* TH, int* TN) {
   double best = -1.0;
@@ -1315,6 +1571,17 @@ static int launch_fprop_tr64(const CUtensorMap& tmX, const CUtensorMap& tmW, con
   }
   const int grid = sm_count();  // every CTA writes its row of the BatchNorm partials (zeros when it has no tile)
   conv_fprop_tr64_kernel<<<grid, kTrThreads, kTrSmem, st>>>(tmX, tmW, p);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+static int launch_fprop_tr128(const CUtensorMap& tmX, const CUtensorMap& tmW, const FpropParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(conv_fprop_tr128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT8Smem));
+    configured = true;
+  }
+  conv_fprop_tr128_kernel<<<sm_count(), kTrThreads, kT8Smem, st>>>(tmX, tmW, p);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -1414,6 +1681,23 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, 64);
     if (rc) return rc;
     return launch_fprop_tr64(tmA, tmB, p, st);
+  }
+  const char* t8_env = getenv("CVB_TR128");  // CVB_TR128=0 keeps the pixel-major halo kernel for cout = 128 (A/B)
+  if (taps == 9 && y.c == 128 && x.w >= kHaloW && x.h >= 2 && !(t8_env && atoi(t8_env) == 0)) {
+    // cout = 128: transposed kernel (channels on M, 256 pixels on N)
+    p.TW = kHaloW; p.TH = kHaloH; p.TN = 1;
+    p.tiles_w = (x.w + kHaloW - 1) / kHaloW;
+    p.tiles_h = (x.h + kHaloH - 1) / kHaloH;
+    p.tiles_n = x.n;
+    p.n_tiles = 1;
+    long long t8_total = 1LL * p.tiles_w * p.tiles_h * p.tiles_n;
+    CVB_REQUIRE(t8_total < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_fprop: too many tiles");
+    p.total_tiles = static_cast<int>(t8_total);
+    rc = make_act_tmap(&tmA, x, kHaloW + 2, kHaloH + 2, 1);
+    if (rc) return rc;
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, 128);
+    if (rc) return rc;
+    return launch_fprop_tr128(tmA, tmB, p, st);
   }
   if (taps == 9 && y.c <= 128 && x.w >= kHaloW && x.h >= 16) {
     // wide-and-shallow layer: halo kernel (one patch fetch per chunk, nine shifted descriptor views)

@@ -133,6 +133,7 @@ def test_conv_cta_pair_kernel_matches_single_cta(ops, cuda, monkeypatch):
     x = to_nhwc_bf16(_rand((n, cin, h, w), cuda, 41))
     wp = ops.pack_weights_fprop(_rand((cout, cin, 3, 3), cuda, 42, scale=(cin * 9) ** -0.5), 9, cout, cin)
     outs, stats = [], []
+    monkeypatch.setenv("CVB_TR128", "0")  # cout = 128 normally takes the transposed kernel
     for mode in ("0", "1"):
         monkeypatch.setenv("CVB_HALO_PAIR", mode)
         y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda)
