@@ -48,7 +48,9 @@ static EncodeTiledFn encode_fn() {
 int make_act_tmap(CUtensorMap* out, const cvb_view& v, int box_w, int box_h, int box_n) {
   EncodeTiledFn fn = encode_fn();
   CVB_REQUIRE(fn != nullptr, CVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  CVB_REQUIRE((v.c % 64) == 0, CVB_ERR_UNSUPPORTED, "GEMM operand view needs channels %% 64 == 0 (got %d)", v.c);
+  // channels need not fill the 64-wide box: what lies beyond v.c is out of bounds = zero-filled, at no HBM cost (the
+  // 27-of-64 im2col'd first layer and the 12-of-64 output layer keep narrow tensors in memory this way)
+  CVB_REQUIRE((v.c % 8) == 0, CVB_ERR_UNSUPPORTED, "GEMM operand view needs channels %% 8 == 0 (got %d)", v.c);
   CVB_REQUIRE(box_w >= 1 && box_w <= 256 && box_h >= 1 && box_h <= 256 && box_n >= 1 && box_n <= 256,
               CVB_ERR_INVALID_ARG, "bad TMA box %dx%dx%d", box_w, box_h, box_n);
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.c), static_cast<cuuint64_t>(v.w), static_cast<cuuint64_t>(v.h),
@@ -70,8 +72,8 @@ int make_act_tmap(CUtensorMap* out, const cvb_view& v, int box_w, int box_h, int
 int make_act_tmap_rowpairs(CUtensorMap* out, const cvb_view& v, int box_w, int box_pairs) {
   EncodeTiledFn fn = encode_fn();
   CVB_REQUIRE(fn != nullptr, CVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  CVB_REQUIRE((v.c % 64) == 0 && (v.h % 2) == 0, CVB_ERR_UNSUPPORTED,
-              "row-pair view needs channels %% 64 == 0 and an even height (got c %d, h %d)", v.c, v.h);
+  CVB_REQUIRE((v.c % 8) == 0 && (v.h % 2) == 0, CVB_ERR_UNSUPPORTED,
+              "row-pair view needs channels %% 8 == 0 and an even height (got c %d, h %d)", v.c, v.h);
   cuuint64_t dims[5] = {static_cast<cuuint64_t>(v.c), static_cast<cuuint64_t>(v.w), 2,
                         static_cast<cuuint64_t>(v.h / 2), static_cast<cuuint64_t>(v.n)};
   cuuint64_t strides[4] = {static_cast<cuuint64_t>(v.sw) * 2, static_cast<cuuint64_t>(v.sh) * 2,

@@ -23,6 +23,7 @@ namespace cvb {
 struct FpropParams {
   int N, H, W;
   int cin_chunks, taps, cin_pad, cout_pad;
+  int ksteps_last;  // K = 16 steps of the last 64-channel chunk that hold real channels (x.c need not fill the chunk)
   int TW, TH, TN;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   uint32_t a_bytes;
@@ -261,11 +262,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + stage * (kABytes >> 4), b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
+        const int ks = kb >= kb_total - p.taps ? p.ksteps_last : 4;  // the producer walks chunks outermost: last chunk = last taps
         if (elect_one()) {
           umma_bf16_lohi(d, a_lo, hi, b_lo, hi, idesc, kb != 0 ? 1u : 0u);
-          umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
-          umma_bf16_lohi(d, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
-          umma_bf16_lohi(d, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+          if (ks > 1) umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+          if (ks > 2) umma_bf16_lohi(d, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+          if (ks > 3) umma_bf16_lohi(d, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
           umma_commit(&empty[stage]);
         }
         __syncwarp();
@@ -1042,11 +1044,12 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const uint32_t w_lo = w_lo0 + sw * (kTrWBytes >> 4);
             const uint32_t x_lo = x_st + (r * kTrPitch + dc) * 8;  // view start: patch row r, column dc (16-byte units)
             const uint32_t first = (chunk | par | v) != 0 ? 1u : 0u;
+            const int ks = chunk == p.cin_chunks - 1 ? p.ksteps_last : 4;
             if (elect_one()) {
               umma_bf16_lohi(d, w_lo, w_hi, x_lo, x_hi, idesc, first);
-              umma_bf16_lohi(d, w_lo + 2, w_hi, x_lo + 2, x_hi, idesc, 1u);
-              umma_bf16_lohi(d, w_lo + 4, w_hi, x_lo + 4, x_hi, idesc, 1u);
-              umma_bf16_lohi(d, w_lo + 6, w_hi, x_lo + 6, x_hi, idesc, 1u);
+              if (ks > 1) umma_bf16_lohi(d, w_lo + 2, w_hi, x_lo + 2, x_hi, idesc, 1u);
+              if (ks > 2) umma_bf16_lohi(d, w_lo + 4, w_hi, x_lo + 4, x_hi, idesc, 1u);
+              if (ks > 3) umma_bf16_lohi(d, w_lo + 6, w_hi, x_lo + 6, x_hi, idesc, 1u);
               umma_commit(&emptyW[sw]);
             }
             __syncwarp();
@@ -1611,15 +1614,20 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_fprop: taps must be 9 or 1 (got %d)", taps);
   CVB_REQUIRE(x.n == y.n && x.h == y.h && x.w == y.w, CVB_ERR_INVALID_ARG,
               "conv_fprop: x %dx%dx%d and y %dx%dx%d spatial shapes differ", x.n, x.h, x.w, y.n, y.h, y.w);
-  CVB_REQUIRE((x.c % 64) == 0 && (y.c % 64) == 0, CVB_ERR_UNSUPPORTED,
-              "conv_fprop: channels must be padded to multiples of 64 (cin %d, cout %d)", x.c, y.c);
+  CVB_REQUIRE((x.c % 16) == 0 && (y.c % 64) == 0, CVB_ERR_UNSUPPORTED,
+              "conv_fprop: cin must be a multiple of 16 and cout padded to a multiple of 64 (cin %d, cout %d)", x.c, y.c);
   CVB_REQUIRE(y.c <= 1024, CVB_ERR_UNSUPPORTED, "conv_fprop: cout %d > 1024", y.c);
 
   FpropParams p;
   memset(&p, 0, sizeof(p));
   p.N = x.n; p.H = x.h; p.W = x.w;
-  p.cin_pad = x.c; p.cout_pad = y.c;
-  p.cin_chunks = x.c / 64;
+  // The weights are packed for cin padded to 64; x itself may stop short of the last chunk (TMA zero-fills the rest of
+  // the box, the MMA issuer skips the all-zero K steps). Only the generic and the cout = 64 kernels implement that.
+  const int cin_pad = (x.c + 63) / 64 * 64;
+  const bool narrow = x.c != cin_pad;
+  p.cin_pad = cin_pad; p.cout_pad = y.c;
+  p.cin_chunks = cin_pad / 64;
+  p.ksteps_last = narrow ? (x.c % 64 + 15) / 16 : 4;
   p.taps = taps;
   pick_tile(x.n, x.h, x.w, &p.TW, &p.TH, &p.TN);
   p.tiles_w = (x.w + p.TW - 1) / p.TW;
@@ -1678,12 +1686,12 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     p.total_tiles = static_cast<int>(tr_total);
     rc = make_act_tmap_rowpairs(&tmA, x, kTrW + 2, kTrI + 1);
     if (rc) return rc;
-    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, 64);
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * cin_pad, 64);
     if (rc) return rc;
     return launch_fprop_tr64(tmA, tmB, p, st);
   }
   const char* t8_env = getenv("CVB_TR128");  // CVB_TR128=0 keeps the pixel-major halo kernel for cout = 128 (A/B)
-  if (taps == 9 && y.c == 128 && x.w >= kHaloW && x.h >= 2 && !(t8_env && atoi(t8_env) == 0)) {
+  if (taps == 9 && y.c == 128 && !narrow && x.w >= kHaloW && x.h >= 2 && !(t8_env && atoi(t8_env) == 0)) {
     // cout = 128: transposed kernel (channels on M, 256 pixels on N)
     p.TW = kHaloW; p.TH = kHaloH; p.TN = 1;
     p.tiles_w = (x.w + kHaloW - 1) / kHaloW;
@@ -1695,11 +1703,11 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     p.total_tiles = static_cast<int>(t8_total);
     rc = make_act_tmap(&tmA, x, kHaloW + 2, kHaloH + 2, 1);
     if (rc) return rc;
-    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, 128);
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * cin_pad, 128);
     if (rc) return rc;
     return launch_fprop_tr128(tmA, tmB, p, st);
   }
-  if (taps == 9 && y.c <= 128 && x.w >= kHaloW && x.h >= 16) {
+  if (taps == 9 && y.c <= 128 && !narrow && x.w >= kHaloW && x.h >= 16) {
     // wide-and-shallow layer: halo kernel (one patch fetch per chunk, nine shifted descriptor views)
     p.TW = kHaloW; p.TH = kHaloH; p.TN = 1;
     p.tiles_w = (x.w + kHaloW - 1) / kHaloW;
@@ -1714,14 +1722,14 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     const char* pe = getenv("CVB_HALO_PAIR");
     const int pair_mode = pe ? atoi(pe) : 0;
     const bool use_pair = pair_mode != 0 && p.total_tiles >= 2 && sm_count() >= 2 && (sm_count() & 1) == 0;
-    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * x.c, use_pair ? y.c / 2 : y.c);
+    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * cin_pad, use_pair ? y.c / 2 : y.c);
     if (rc) return rc;
     if (use_pair) return y.c == 64 ? launch_fprop_halo2<64>(tmA, tmB, p, st) : launch_fprop_halo2<128>(tmA, tmB, p, st);
     return y.c == 64 ? launch_fprop_halo<64>(tmA, tmB, p, st) : launch_fprop_halo<128>(tmA, tmB, p, st);
   }
   rc = make_act_tmap(&tmA, x, p.TW, p.TH, p.TN);
   if (rc) return rc;
-  rc = make_mat_tmap(&tmB, wpack, y.c, 1LL * taps * x.c, BN);
+  rc = make_mat_tmap(&tmB, wpack, y.c, 1LL * taps * cin_pad, BN);
   if (rc) return rc;
   switch (BN) {
     case 256: return launch_fprop<256>(tmA, tmB, p, st);
@@ -1731,6 +1739,6 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
 }
 
 extern "C" int cvb_conv3x3_fprop_fuses_bwd_stats(cvb_view x, cvb_view y, int taps) {
-  if (x.n != y.n || x.h != y.h || x.w != y.w || (x.c % 64) != 0) return 0;
+  if (x.n != y.n || x.h != y.h || x.w != y.w || (x.c % 16) != 0) return 0;
   return uses_tr64(x, y, taps) ? 1 : 0;
 }

@@ -528,8 +528,11 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_wgrad: taps must be 9 or 1 (got %d)", taps);
   CVB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w, CVB_ERR_INVALID_ARG,
               "conv_wgrad: x %dx%dx%d and dy %dx%dx%d spatial shapes differ", x.n, x.h, x.w, dy.n, dy.h, dy.w);
-  CVB_REQUIRE((x.c % 64) == 0 && (dy.c % 64) == 0, CVB_ERR_UNSUPPORTED,
-              "conv_wgrad: channels must be padded to multiples of 64 (cin %d, cout %d)", x.c, dy.c);
+  CVB_REQUIRE((x.c % 16) == 0 && (dy.c % 64) == 0, CVB_ERR_UNSUPPORTED,
+              "conv_wgrad: cin must be a multiple of 16 and cout padded to a multiple of 64 (cin %d, cout %d)", x.c, dy.c);
+  // x may stop short of its last 64-channel chunk (the im2col'd first layer keeps 32 channels in memory): TMA zero-fills
+  // the rest of the box, the corresponding gradient rows come out as zeros and are never copied out
+  const int cin_pad = (x.c + 63) / 64 * 64;
   WgradParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.N = x.n; p.H = x.h; p.W = x.w;
@@ -551,7 +554,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   CVB_REQUIRE(tiles < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_wgrad: too many pixel tiles");
   p.total_tiles = static_cast<int>(tiles);
   p.taps = taps;
-  p.cin_pad = x.c;
+  p.cin_pad = cin_pad;
   p.cout_pad = dy.c;
   const int BN = (dy.c % 256 == 0) ? 256 : ((dy.c % 128 == 0) ? 128 : 64);
   plan->BN = BN;
@@ -563,7 +566,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
     p.T = 9;
     p.n_tap_groups = 1;
     p.n_co_tiles = 1;
-    p.n_ci_tiles = x.c / 64;
+    p.n_ci_tiles = cin_pad / 64;
     p.stage_bytes = kRsStageBytes;
     p.stages = kRsStages;
     p.items = p.n_ci_tiles;
@@ -578,10 +581,10 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
     p.slots = slots_rs;
     plan->grid = p.grid;
     plan->smem = 1024 + kRsStages * kRsStageBytes + 256;
-    plan->ws_bytes = 1LL * slots_rs * taps * x.c * dy.c * 4;
+    plan->ws_bytes = 1LL * slots_rs * taps * cin_pad * dy.c * 4;
     return CVB_OK;
   }
-  p.CM = (x.c % 128 == 0) ? 2 : 1;
+  p.CM = (cin_pad % 128 == 0) ? 2 : 1;
   // accumulators: accs * BN <= 512 TMEM columns, accs <= kMaxAccs; one accumulator = two 64-row atoms
   int max_accs = 512 / BN;
   if (max_accs > kMaxAccs) max_accs = kMaxAccs;
@@ -590,7 +593,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.T = (taps + p.n_tap_groups - 1) / p.n_tap_groups;  // balanced groups
   p.n_tap_groups = (taps + p.T - 1) / p.T;
   p.n_co_tiles = dy.c / BN;
-  p.n_ci_tiles = x.c / (64 * p.CM);
+  p.n_ci_tiles = cin_pad / (64 * p.CM);
   p.stage_bytes = p.CM * kWPatchStride + (BN / 64) * kWDyBytes;
   p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
@@ -608,7 +611,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.slots = slots;
   plan->grid = p.grid;
   plan->smem = 1024 + p.stages * p.stage_bytes + 256;
-  plan->ws_bytes = 1LL * slots * taps * x.c * dy.c * 4;
+  plan->ws_bytes = 1LL * slots * taps * cin_pad * dy.c * 4;
   return CVB_OK;
 }
 
@@ -681,15 +684,16 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   if (rc) return rc;
   }
   // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
+  const int cin_pad = plan.p.cin_pad;
   int bci = 32;
-  while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((x.c + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
+  while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
   if (plan.p.slots > 1) {
-    const long long n4 = 1LL * taps * x.c * dy.c / 4;
+    const long long n4 = 1LL * taps * cin_pad * dy.c / 4;
     wgrad_partsum_kernel<<<ew_grid(n4, 256, 16), 256, 0, st>>>(plan.p.ws, plan.p, plan.BN);
     CVB_LAUNCH_CHECK();
   }
   dim3 rgrid((dy.c + 31) / 32, (x.c + bci - 1) / bci);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, x.c, dy.c, cout, cin_eff,
+  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, cin_pad, dy.c, cout, cin_eff,
                                                                           bci, dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

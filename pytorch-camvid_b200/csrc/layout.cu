@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kThreads) im2col3x3_c3_kernel(const float* __r
     __nv_bfloat16* dp = dst.p + poff(dst, i);
 #pragma unroll
     for (int cv = 0; cv < 8; ++cv) {
+      if (cv * 8 >= dst.c) break;  // 32-channel destination: the padding beyond channel 31 is never materialised
       uint4 u = make_uint4(0, 0, 0, 0);
       if (cv < 4) {
         u.x = pk2(f[cv * 8 + 0], f[cv * 8 + 1]);
@@ -238,7 +239,7 @@ extern "C" int cvb_im2col3x3_nchw_f32(const float* src, int c_src, cvb_view dst,
   CVB_REQUIRE(src && c_src > 0 && c_src * 9 <= dst.c, CVB_ERR_INVALID_ARG,
               "im2col3x3: 9*c_src=%d does not fit the %d destination channels", c_src * 9, dst.c);
   long long total = 1LL * dst.n * dst.h * dst.w;
-  if (c_src == 3 && dst.c == 64)
+  if (c_src == 3 && (dst.c == 64 || dst.c == 32))
     im2col3x3_c3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, to_dev(dst));
   else
     im2col3x3_kernel<<<ew_grid(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, c_src,

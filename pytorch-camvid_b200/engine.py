@@ -37,10 +37,13 @@ class Block:
         self.plan, self.name, self.conv, self.bn = plan, name, conv, bn
         self.x, self.a, self.taps = x, a, taps
         self.cin, self.cout = conv.in_channels, conv.out_channels
-        n, h, w, self.cin_pad = x.shape
+        n, h, w, cin_mem = x.shape
+        # channels of x in memory may stop short of the 64-wide GEMM chunk (the im2col'd first layer keeps 32): TMA
+        # zero-fills the rest of the box; the packed weights are always padded to 64
+        self.cin_pad = pad64(cin_mem)
         self.cout_pad = a.shape[3]
         assert a.shape[:3] == x.shape[:3], (name, a.shape, x.shape)
-        assert self.cout_pad == pad64(self.cout) and self.cin_pad % 64 == 0
+        assert self.cout_pad == pad64(self.cout) and cin_mem % 16 == 0
         self.count = n * h * w
         dev = x.device
         self.y = torch.empty(n, h, w, self.cout_pad, dtype=torch.bfloat16, device=dev)  # conv output, later dy
@@ -56,6 +59,7 @@ class Block:
         # for the 12-class output layer, whose 64-channel-padded full-resolution tensors would otherwise cost 4x.
         self.ce = min(self.cout_pad, (self.cout + 7) // 8 * 8)
         self.y_e, self.a_e = self.y[..., :self.ce], self.a[..., :self.ce]
+        self.dy_k = self.y[..., :min(self.cout_pad, (self.cout + 15) // 16 * 16)]
         self.c_ratio = self.cout / self.ce
         # offsets into the flat gradient buffer, assigned by the plan
         self.g_w = self.g_b = self.g_gamma = self.g_beta = None
@@ -149,13 +153,15 @@ class Block:
             if consumer is not None and FUSE_BWD_STATS:
                 if self._fuses is None:
                     self._fuses = (consumer.ce == consumer.cout_pad == dx.shape[3]
-                                   and ops.conv3x3_fuses_bwd_stats(self.y, dx))
+                                   and ops.conv3x3_fuses_bwd_stats(self.dy_k, dx))
                 fused = self._fuses
+            # dy of a padded layer (12 -> 64 output channels) is read through its real channels only: the data gradient
+            # then skips the all-zero K steps (self.dy_k is a 16-channel-granular slice of y)
             if fused:
-                ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops,
+                ops.conv3x3(self.dy_k, self.wd, dx, algo_flops=self.flops,
                             bwd=(consumer.y_e, consumer.vec[2], consumer.vec[3], p.parts_view(consumer.ce)))
             else:
-                ops.conv3x3(self.y, self.wd, dx, algo_flops=self.flops)
+                ops.conv3x3(self.dy_k, self.wd, dx, algo_flops=self.flops)
         if p.wstream is not None:
             # The side stream picks the weight gradient up AFTER the data gradient: started together the two tensor-bound
             # kernels only split the SMs between them (measured: same finish time as back to back) and the HBM-bound
@@ -304,7 +310,7 @@ class UNetPlan(Plan):
             hs.append(hs[-1] // 2)
             ws.append(ws[-1] // 2)
         ch = [64, 128, 256, 512, 1024]
-        self.cols = self.buf(h, w, 64)
+        self.cols = self.buf(h, w, min(64, (9 * m.input_channels + 15) // 16 * 16))  # im2col of the input: 27 real channels of 32
         # concat buffers at levels 0..3: channels [0, ch[l]) = upsampled branch, [ch[l], 2 ch[l]) = encoder skip
         self.cat = [self.buf(hs[l], ws[l], 2 * ch[l], zero=True) for l in range(4)]
         self.dcat = [self.buf(hs[l], ws[l], 2 * ch[l]) for l in range(4)]
@@ -424,7 +430,7 @@ class SegNetPlan(Plan):
         self.class_num = m.class_num
         encs = [m.encoder1, m.encoder2, m.encoder3, m.encoder4, m.encoder5]
         decs = [m.decoder5, m.decoder4, m.decoder3, m.decoder2, m.decoder1]
-        self.cols = self.buf(h, w, 64)
+        self.cols = self.buf(h, w, min(64, (9 * m.input_channels + 15) // 16 * 16))  # im2col of the input: 27 real channels of 32
         self.stages = []  # encoder stages: blocks, activations, pooled, code
         x = self.cols
         ch_, cw_ = h, w

@@ -100,12 +100,13 @@ def test_conv_fprop_eval_epilogue_and_strided_output(ops, cuda):
     assert (big[:, h] == 3).all() and (big[..., :64] == 3).all() and (big[..., 128:] == 3).all()
 
 
-def test_conv_first_layer_im2col(ops, cuda):
+@pytest.mark.parametrize("cols_c", [64, 32])  # 32: narrow im2col buffer, the rest of the K chunk is TMA zero fill
+def test_conv_first_layer_im2col(ops, cuda, cols_c):
     n, h, w, cin, cout = 2, 20, 28, 3, 64
     x = _rand((n, cin, h, w), cuda, 6)
     wt = _rand((cout, cin, 3, 3), cuda, 7, scale=27 ** -0.5)
     ref = F.conv2d(x, wt, padding=1)
-    cols = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    cols = torch.empty(n, h, w, cols_c, dtype=torch.bfloat16, device=cuda)
     ops.im2col3x3(x, cols)
     wp = ops.pack_weights_fprop(wt, 1, 64, 64)
     y = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
@@ -171,6 +172,21 @@ def test_conv_dgrad_emits_consumer_bn_backward_statistics(ops, cuda, n, h, w, ci
     assert rel_err(got[0], want[0]) < 1e-4 and rel_err(got[1], want[1]) < 1e-4
 
 
+
+def test_conv_dgrad_narrow_dy_skips_zero_k_steps(ops, cuda):
+    """Output layer (12 classes padded to 64 channels of dy): reading dy through its first 16 channels only (the rest is
+    TMA zero fill, the all-zero K steps are skipped) must give the same data gradient as the padded view."""
+    n, h, w, cin, cout = 2, 36, 40, 64, 12
+    wt = _rand((cout, cin, 3, 3), cuda, 51, scale=(cin * 9) ** -0.5)
+    dyp = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    dyp[..., :cout] = to_nhwc_bf16(_rand((n, cout, h, w), cuda, 52))
+    wd = ops.pack_weights_dgrad(wt, 64, cin)
+    full, narrow = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=cuda), torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=cuda)
+    ops.conv3x3(dyp, wd, full)
+    ops.conv3x3(dyp[..., :16], wd, narrow)
+    assert torch.equal(full, narrow)
+
+
 WGRAD_CASES = [
     (2, 16, 24, 64, 64),
     (2, 23, 31, 128, 64),
@@ -198,13 +214,14 @@ def test_conv_wgrad(ops, cuda, n, h, w, cin, cout):
     assert rel_err(dw, ref) < 1e-4  # fp32 accumulate of exact bf16 products, fp32 output
 
 
-def test_conv_wgrad_first_layer_and_padded_cout(ops, cuda):
+@pytest.mark.parametrize("cols_c", [64, 32])
+def test_conv_wgrad_first_layer_and_padded_cout(ops, cuda, cols_c):
     n, h, w = 2, 20, 28
     x = _rand((n, 3, h, w), cuda, 14)
     wt = _rand((64, 3, 3, 3), cuda, 15).requires_grad_(True)
     dy = _rand((n, 64, h, w), cuda, 16)
     (ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
-    cols = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
+    cols = torch.empty(n, h, w, cols_c, dtype=torch.bfloat16, device=cuda)
     ops.im2col3x3(x, cols)
     dw = torch.empty(64, 3, 3, 3, device=cuda)
     ops.conv3x3_wgrad(cols, to_nhwc_bf16(dy), dw, taps=1)
