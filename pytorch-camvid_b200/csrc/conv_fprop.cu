@@ -23,6 +23,7 @@ namespace cvb {
 struct FpropParams {
   int N, H, W;
   int cin_chunks, taps, cin_pad, cout_pad;
+  int cout_store;   // channels of y that exist in memory (<= cout_pad; the transposed cout = 64 kernel stores only these)
   int ksteps_last;  // K = 16 steps of the last 64-channel chunk that hold real channels (x.c need not fill the chunk)
   int TW, TH, TN;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
@@ -1164,7 +1165,7 @@ conv_fprop_tr64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(tb_st + t * 64), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
         }
         __syncwarp();
-        if (!(p.debug & 1) && jj < wvalid) {
+        if (!(p.debug & 1) && jj < wvalid && (wq & 1) * 32 + part * 8 < p.cout_store) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint4 o;
@@ -1596,7 +1597,7 @@ static bool uses_tr64(const cvb_view& x, const cvb_view& y, int taps) {
     const char* e = getenv("CVB_TR64");
     tr_mode = e ? atoi(e) : 1;
   }
-  return taps == 9 && y.c == 64 && (x.h % 2) == 0 && x.w >= kTrW && tr_mode != 0;
+  return taps == 9 && y.c <= 64 && (x.h % 2) == 0 && x.w >= kTrW && tr_mode != 0;
 }
 
 }  // namespace cvb
@@ -1614,8 +1615,14 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_fprop: taps must be 9 or 1 (got %d)", taps);
   CVB_REQUIRE(x.n == y.n && x.h == y.h && x.w == y.w, CVB_ERR_INVALID_ARG,
               "conv_fprop: x %dx%dx%d and y %dx%dx%d spatial shapes differ", x.n, x.h, x.w, y.n, y.h, y.w);
-  CVB_REQUIRE((x.c % 16) == 0 && (y.c % 64) == 0, CVB_ERR_UNSUPPORTED,
-              "conv_fprop: cin must be a multiple of 16 and cout padded to a multiple of 64 (cin %d, cout %d)", x.c, y.c);
+  CVB_REQUIRE((x.c % 16) == 0 && (y.c % 8) == 0, CVB_ERR_UNSUPPORTED,
+              "conv_fprop: cin must be a multiple of 16 and cout a multiple of 8 (cin %d, cout %d)", x.c, y.c);
+  // y may hold fewer channels than the 64-padded GEMM computes (12 classes -> 16 channels in memory): only the
+  // transposed cout = 64 kernel stores a channel subset
+  const int cout_pad = (y.c + 63) / 64 * 64;
+  const bool narrow_out = y.c != cout_pad;
+  CVB_REQUIRE(!narrow_out || uses_tr64(x, y, taps), CVB_ERR_UNSUPPORTED,
+              "conv_fprop: cout %d is not a multiple of 64 and the cout = 64 kernel does not apply to these views", y.c);
   CVB_REQUIRE(y.c <= 1024, CVB_ERR_UNSUPPORTED, "conv_fprop: cout %d > 1024", y.c);
 
   FpropParams p;
@@ -1625,7 +1632,7 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   // the box, the MMA issuer skips the all-zero K steps). Only the generic and the cout = 64 kernels implement that.
   const int cin_pad = (x.c + 63) / 64 * 64;
   const bool narrow = x.c != cin_pad;
-  p.cin_pad = cin_pad; p.cout_pad = y.c;
+  p.cin_pad = cin_pad; p.cout_pad = cout_pad; p.cout_store = y.c;
   p.cin_chunks = cin_pad / 64;
   p.ksteps_last = narrow ? (x.c % 64 + 15) / 16 : 4;
   p.taps = taps;
@@ -1633,8 +1640,8 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
   p.tiles_w = (x.w + p.TW - 1) / p.TW;
   p.tiles_h = (x.h + p.TH - 1) / p.TH;
   p.tiles_n = (x.n + p.TN - 1) / p.TN;
-  const int BN = (y.c % 256 == 0) ? 256 : ((y.c % 128 == 0) ? 128 : 64);
-  p.n_tiles = y.c / BN;
+  const int BN = (cout_pad % 256 == 0) ? 256 : ((cout_pad % 128 == 0) ? 128 : 64);
+  p.n_tiles = cout_pad / BN;
   long long total = 1LL * p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   CVB_REQUIRE(total < (1LL << 31), CVB_ERR_UNSUPPORTED, "conv_fprop: too many tiles");
   p.total_tiles = static_cast<int>(total);
@@ -1668,7 +1675,7 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     rc = check_view(ep->bwd_y, "conv_fprop.bwd_y");
     if (rc) return rc;
     CVB_REQUIRE(same_shape(ep->bwd_y, y), CVB_ERR_INVALID_ARG, "conv_fprop: bwd_y and y shapes differ");
-    CVB_REQUIRE(uses_tr64(x, y, taps), CVB_ERR_UNSUPPORTED,
+    CVB_REQUIRE(uses_tr64(x, y, taps) && !narrow_out, CVB_ERR_UNSUPPORTED,
                 "conv_fprop: no kernel with the bwd_* epilogue for these views (ask cvb_conv3x3_fprop_fuses_bwd_stats)");
     p.by = static_cast<const __nv_bfloat16*>(ep->bwd_y.ptr);
     p.bysn = ep->bwd_y.sn; p.bysh = ep->bwd_y.sh; p.bysw = ep->bwd_y.sw;
@@ -1686,7 +1693,7 @@ extern "C" int cvb_conv3x3_fprop(cvb_view x, const void* wpack, int taps, cvb_vi
     p.total_tiles = static_cast<int>(tr_total);
     rc = make_act_tmap_rowpairs(&tmA, x, kTrW + 2, kTrI + 1);
     if (rc) return rc;
-    rc = make_mat_tmap(&tmB, wpack, y.c, 9LL * cin_pad, 64);
+    rc = make_mat_tmap(&tmB, wpack, cout_pad, 9LL * cin_pad, 64);
     if (rc) return rc;
     return launch_fprop_tr64(tmA, tmB, p, st);
   }

@@ -528,8 +528,11 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_wgrad: taps must be 9 or 1 (got %d)", taps);
   CVB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w, CVB_ERR_INVALID_ARG,
               "conv_wgrad: x %dx%dx%d and dy %dx%dx%d spatial shapes differ", x.n, x.h, x.w, dy.n, dy.h, dy.w);
-  CVB_REQUIRE((x.c % 16) == 0 && (dy.c % 64) == 0, CVB_ERR_UNSUPPORTED,
-              "conv_wgrad: cin must be a multiple of 16 and cout padded to a multiple of 64 (cin %d, cout %d)", x.c, dy.c);
+  CVB_REQUIRE((x.c % 16) == 0 && (dy.c % 16) == 0, CVB_ERR_UNSUPPORTED,
+              "conv_wgrad: cin and cout must be multiples of 16 (cin %d, cout %d)", x.c, dy.c);
+  // dy may hold fewer channels than the 64-padded GEMM (12 classes -> 16 channels in memory): zero fill as for x; only the
+  // cout = 64 row-shift kernel is used that way
+  const int cout_pad = (dy.c + 63) / 64 * 64;
   // x may stop short of its last 64-channel chunk (the im2col'd first layer keeps 32 channels in memory): TMA zero-fills
   // the rest of the box, the corresponding gradient rows come out as zeros and are never copied out
   const int cin_pad = (x.c + 63) / 64 * 64;
@@ -538,7 +541,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.N = x.n; p.H = x.h; p.W = x.w;
   p.tiles_w = (x.w + kWTileW - 1) / kWTileW;
   p.th = kWTileH;
-  if (x.h < 2 * kWTileH && !(taps == 9 && dy.c == 64)) {
+  if (x.h < 2 * kWTileH && !(taps == 9 && cout_pad == 64)) {
     // small images (22 or 11 rows at the bottom of the networks): a 16-row tile would be up to a third padding
     int best = (x.h + kWTileH - 1) / kWTileH * kWTileH;
     for (int th = kWTileH - 2; th >= 8; th -= 2) {
@@ -555,12 +558,14 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.total_tiles = static_cast<int>(tiles);
   p.taps = taps;
   p.cin_pad = cin_pad;
-  p.cout_pad = dy.c;
-  const int BN = (dy.c % 256 == 0) ? 256 : ((dy.c % 128 == 0) ? 128 : 64);
+  p.cout_pad = cout_pad;
+  const int BN = (cout_pad % 256 == 0) ? 256 : ((cout_pad % 128 == 0) ? 128 : 64);
   plan->BN = BN;
   // CVB_WGRAD_RS=0 keeps the N = 64 kernel for cout = 64 (A/B measurements); read per call
   const char* rs_env = getenv("CVB_WGRAD_RS");
-  plan->rowshift = taps == 9 && dy.c == 64 && !(rs_env && atoi(rs_env) == 0);
+  plan->rowshift = taps == 9 && cout_pad == 64 && !(rs_env && atoi(rs_env) == 0);
+  CVB_REQUIRE(plan->rowshift || dy.c == cout_pad, CVB_ERR_UNSUPPORTED,
+              "conv_wgrad: cout %d is not a multiple of 64 and the cout = 64 kernel does not apply", dy.c);
   if (plan->rowshift) {
     p.CM = 1;
     p.T = 9;
@@ -581,7 +586,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
     p.slots = slots_rs;
     plan->grid = p.grid;
     plan->smem = 1024 + kRsStages * kRsStageBytes + 256;
-    plan->ws_bytes = 1LL * slots_rs * taps * cin_pad * dy.c * 4;
+    plan->ws_bytes = 1LL * slots_rs * taps * cin_pad * cout_pad * 4;
     return CVB_OK;
   }
   p.CM = (cin_pad % 128 == 0) ? 2 : 1;
@@ -592,7 +597,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.n_tap_groups = (taps + max_taps - 1) / max_taps;
   p.T = (taps + p.n_tap_groups - 1) / p.n_tap_groups;  // balanced groups
   p.n_tap_groups = (taps + p.T - 1) / p.T;
-  p.n_co_tiles = dy.c / BN;
+  p.n_co_tiles = cout_pad / BN;
   p.n_ci_tiles = cin_pad / (64 * p.CM);
   p.stage_bytes = p.CM * kWPatchStride + (BN / 64) * kWDyBytes;
   p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
@@ -611,7 +616,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.slots = slots;
   plan->grid = p.grid;
   plan->smem = 1024 + p.stages * p.stage_bytes + 256;
-  plan->ws_bytes = 1LL * slots * taps * cin_pad * dy.c * 4;
+  plan->ws_bytes = 1LL * slots * taps * cin_pad * cout_pad * 4;
   return CVB_OK;
 }
 
@@ -684,16 +689,16 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   if (rc) return rc;
   }
   // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
-  const int cin_pad = plan.p.cin_pad;
+  const int cin_pad = plan.p.cin_pad, cout_pad = plan.p.cout_pad;
   int bci = 32;
-  while (bci > 2 && 1LL * ((dy.c + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
+  while (bci > 2 && 1LL * ((cout_pad + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
   if (plan.p.slots > 1) {
-    const long long n4 = 1LL * taps * cin_pad * dy.c / 4;
+    const long long n4 = 1LL * taps * cin_pad * cout_pad / 4;
     wgrad_partsum_kernel<<<ew_grid(n4, 256, 16), 256, 0, st>>>(plan.p.ws, plan.p, plan.BN);
     CVB_LAUNCH_CHECK();
   }
-  dim3 rgrid((dy.c + 31) / 32, (x.c + bci - 1) / bci);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, cin_pad, dy.c, cout, cin_eff,
+  dim3 rgrid((cout_pad + 31) / 32, (x.c + bci - 1) / bci);
+  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, cin_pad, cout_pad, cout, cin_eff,
                                                                           bci, dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;

@@ -30,6 +30,12 @@ OVERLAP_WGRAD = True
 FUSE_BWD_STATS = os.environ.get("CVB_FUSE_BWD", "0") != "0"
 
 
+def narrow_channels(c):
+    """Channels kept in memory for a layer of c outputs: 16-channel granularity (one MMA K step) up to the 64-wide GEMM
+    chunk. TMA zero-fills the rest of the box, so 12 classes cost 16 channels of HBM traffic instead of 64."""
+    return min(pad64(c), (c + 15) // 16 * 16)
+
+
 class Block:
     """conv3x3(pad 1, bias) + BatchNorm2d + ReLU on NHWC bf16 views."""
 
@@ -41,25 +47,28 @@ class Block:
         # channels of x in memory may stop short of the 64-wide GEMM chunk (the im2col'd first layer keeps 32): TMA
         # zero-fills the rest of the box; the packed weights are always padded to 64
         self.cin_pad = pad64(cin_mem)
-        self.cout_pad = a.shape[3]
+        self.cout_pad = pad64(self.cout)  # GEMM padding; the activation buffers may hold fewer channels (12 -> 16)
+        c_mem = a.shape[3]
         assert a.shape[:3] == x.shape[:3], (name, a.shape, x.shape)
-        assert self.cout_pad == pad64(self.cout) and cin_mem % 16 == 0
+        assert c_mem in (self.cout_pad, narrow_channels(self.cout)) and cin_mem % 16 == 0
         self.count = n * h * w
         dev = x.device
-        self.y = torch.empty(n, h, w, self.cout_pad, dtype=torch.bfloat16, device=dev)  # conv output, later dy
+        self.y = torch.empty(n, h, w, c_mem, dtype=torch.bfloat16, device=dev)  # conv output, later dy
         self.vec = torch.zeros(4, self.cout_pad, device=dev)  # mean, invstd, scale, shift
         self.coef = torch.zeros(3, self.cout_pad, device=dev)
         self.wf = torch.empty(self.cout_pad, taps * self.cin_pad, dtype=torch.bfloat16, device=dev)
         self.wd = None if taps == 1 else torch.empty(self.cin_pad, 9 * self.cout_pad, dtype=torch.bfloat16, device=dev)
         self.wf_version = self.wd_version = None
-        self.ws_bytes = ops.conv3x3_wgrad_workspace_bytes(x, self.y, taps)
         self.flops = 2.0 * 9 * self.cin * self.cout * self.count  # algorithmic FLOPs of one pass (un-padded channels)
         # Elementwise kernels only touch the channels that exist (rounded up to the 16-byte vector): the padded output
         # channels of y are exact zeros (zero weight rows), stay zero as dy, and are never read as activations. Matters
         # for the 12-class output layer, whose 64-channel-padded full-resolution tensors would otherwise cost 4x.
-        self.ce = min(self.cout_pad, (self.cout + 7) // 8 * 8)
+        self.ce = min(c_mem, (self.cout + 7) // 8 * 8)
         self.y_e, self.a_e = self.y[..., :self.ce], self.a[..., :self.ce]
-        self.dy_k = self.y[..., :min(self.cout_pad, (self.cout + 15) // 16 * 16)]
+        self.dy_k = self.y[..., :min(c_mem, narrow_channels(self.cout))]
+        # the weight gradient reads dy through 16-channel granularity too when the layer is narrower than 64 channels
+        self.dy_w = self.dy_k if (taps == 9 and self.cout_pad == 64) else self.y
+        self.ws_bytes = ops.conv3x3_wgrad_workspace_bytes(x, self.dy_w, taps)
         self.c_ratio = self.cout / self.ce
         # offsets into the flat gradient buffer, assigned by the plan
         self.g_w = self.g_b = self.g_gamma = self.g_beta = None
@@ -131,7 +140,7 @@ class Block:
         p, v = self.plan, self.vec
         parts = p.parts_view(self.ce)  # the reduce kernel lays its partial rows out with the view's channel count
         ops.WORK_SCALE = self.c_ratio
-        if self.ce != self.cout_pad:
+        if self.ce != da.shape[3]:
             da = da[..., :self.ce]
         rows = p.stat_rows
         if not stats_ready:
@@ -146,7 +155,7 @@ class Block:
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
         # (conv bias feeds a batch-stat BatchNorm: its gradient is exactly 0 -- the flat buffer starts zeroed)
         if p.wstream is None:
-            ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+            ops.conv3x3_wgrad(self.x, self.dy_w, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         fused = False
         if dx is not None:
             self._pack_d()
@@ -171,7 +180,7 @@ class Block:
             ready.record()
             p.wstream.wait_event(ready)
             with torch.cuda.stream(p.wstream):
-                ops.conv3x3_wgrad(self.x, self.y, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+                ops.conv3x3_wgrad(self.x, self.dy_w, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
         return fused
 
 
@@ -356,7 +365,9 @@ class UNetPlan(Plan):
             self.dec.append(dict(src=x, dsrc=dx, up=up, dup=dup, win=win, bu=bu, b0=b0, b1=b1, m0=m0, m1=m1,
                                  dm0=torch.empty_like(m0), dm1=torch.empty_like(m1), level=l))
             x, dx = m1, self.dec[-1]["dm1"]
-        self.out_a = self.buf(h, w, pad64(self.class_num))
+        # 12 classes: 16 channels in memory where the transposed cout = 64 kernel runs (even height), else 64
+        out_c = narrow_channels(self.class_num) if (h % 2 == 0 and w >= 8) else pad64(self.class_num)
+        self.out_a = self.buf(h, w, out_c)
         self.d_out_a = torch.empty_like(self.out_a)
         self.b_out = self.add("output", m.output.conv, x, self.out_a)
         self.finish()
@@ -458,7 +469,9 @@ class SegNetPlan(Plan):
             blocks, acts, dacts = [], [], []
             xin = un
             for j, bc in enumerate(seq):
-                a = self.buf(hh, ww, pad64(bc.conv.out_channels))
+                last = i == len(decs) - 1 and j == len(seq) - 1  # the class logits: 16 channels in memory (see UNetPlan)
+                narrow = last and hh % 2 == 0 and ww >= 8
+                a = self.buf(hh, ww, narrow_channels(bc.conv.out_channels) if narrow else pad64(bc.conv.out_channels))
                 blocks.append(self.add(f"decoder{5 - i}.{j}", (bc.conv, bc.bn), xin, a))
                 acts.append(a)
                 dacts.append(torch.empty_like(a))
