@@ -17,7 +17,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_dynamic", "sm__cycles_active.avg"]
 
 
-FAMILIES = {"conv3x3_fprop": ("conv_fprop_kernel", "conv_fprop_halo_kernel", "conv_fprop_halo2_kernel", "conv_fprop_tr64_kernel"),
+FAMILIES = {"conv3x3_fprop": ("conv_fprop_kernel", "conv_fprop_halo_kernel", "conv_fprop_halo2_kernel", "conv_fprop_tr64_kernel",
+                              "conv_fprop_tr128_kernel"),
             "conv3x3_wgrad": ("conv_wgrad_kernel", "conv_wgrad_rs64_kernel")}
 
 
