@@ -607,6 +607,18 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.total_units = 1LL * p.items * p.total_tiles;
   // one CTA per SM, each an equal share of the flattened (item, tile) space; never more CTAs than units
   p.grid = static_cast<int>(p.total_units < sm_count() ? p.total_units : sm_count());
+  {
+    // Lockstep: with a grid that is a multiple of the item count every item is cut at the same tile boundaries, so the
+    // CTAs of different items sweep the SAME pixel tiles at the same time and the x / dy tiles they share are fetched
+    // from HBM once and hit in L2 by the others. With the plain 148-way cut the items drift apart and the big layers
+    // re-read their operands 2.6-3.4x from HBM (ncu: 1.2 GB per launch against 354 MB on 256->128 at 180x240), which
+    // made them HBM-bound. Taken when it idles at most 7 % of the SMs. CVB_WGRAD_LOCKSTEP=0 disables (A/B).
+    const char* ls_env = getenv("CVB_WGRAD_LOCKSTEP");
+    const int S = p.items > 0 ? sm_count() / p.items : 0;
+    if (!(ls_env && atoi(ls_env) == 0) && p.items >= 2 && S >= 1 && S <= p.total_tiles &&
+        p.items * S * 100 >= sm_count() * 93)
+      p.grid = p.items * S;
+  }
   int slots = 1;
   for (int item = 0; item < p.items; ++item) {
     const long long u0 = 1LL * item * p.total_tiles;
