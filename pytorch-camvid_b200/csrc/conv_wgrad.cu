@@ -35,6 +35,7 @@ constexpr int kWPatchStride = 23552;                      // rounded up to 1 KB
 constexpr int kWDyBytes = kWTileW * kWTileH * 128;        // 16384 per 64-channel unit
 constexpr int kWgradSmemBudget = 225 * 1024;
 constexpr int kMaxAccs = 8;
+constexpr int kMaxWaves = 4;
 
 struct WgradParams {
   int N, H, W;
@@ -46,6 +47,10 @@ struct WgradParams {
   int n_co_tiles, n_ci_tiles, n_tap_groups, items;
   int grid;               // CTAs = ranges of the flattened (item, tile) space
   long long total_units;  // items * total_tiles
+  // Waves (conv_wgrad_kernel): the items are processed in up to kMaxWaves groups, each a stream-K partition of its own
+  // whose grid is a multiple of its item count (lockstep, see plan_wgrad); CTA c takes part in wave w if c < wave_grid[w].
+  int n_waves;
+  int wave_item0[4], wave_items[4], wave_grid[4];
   int slots;              // workspace parts per item
   int stages, stage_bytes;
   float* ws;  // [slots][taps][cin_pad][cout_pad]; part k of an item lives in slot k (k < parts of that item)
@@ -93,9 +98,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const long long u_begin = sk_begin(p.total_units, p.grid, blockIdx.x);
-  const long long u_end = sk_begin(p.total_units, p.grid, blockIdx.x + 1);
-  const int item_first = static_cast<int>(u_begin / p.total_tiles);
+  // per wave: this CTA's unit range [u_begin, u_end) of the wave's flattened (local item, tile) space
+#define CVB_WAVE_RANGE(w)                                                                                         \
+  const long long wave_units = 1LL * p.wave_items[w] * p.total_tiles;                                             \
+  const bool in_wave = static_cast<int>(blockIdx.x) < p.wave_grid[w];                                             \
+  const long long u_begin = in_wave ? sk_begin(wave_units, p.wave_grid[w], blockIdx.x) : 0;                       \
+  const long long u_end = in_wave ? sk_begin(wave_units, p.wave_grid[w], blockIdx.x + 1) : 0;                     \
+  const int item_first = static_cast<int>(u_begin / p.total_tiles);                                               \
   const int item_last = u_end > u_begin ? static_cast<int>((u_end - 1) / p.total_tiles) : item_first - 1;
 
   if (warp == 0 && lane == 0) {
@@ -126,10 +135,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.CM) * (p.th + 2) * kWPitch * 128 + b_units * p.th * kWTileW * 128;
-      for (int item = item_first; item <= item_last; ++item) {
+      for (int w = 0; w < p.n_waves; ++w) {
+      CVB_WAVE_RANGE(w)
+      for (int litem = item_first; litem <= item_last; ++litem) {
+        const int item = p.wave_item0[w] + litem;
         const int co_tile = item % p.n_co_tiles;
         const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
-        const long long base = 1LL * item * p.total_tiles;
+        const long long base = 1LL * litem * p.total_tiles;
         const int tile_begin = static_cast<int>(max(u_begin, base) - base);
         const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
         for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -153,6 +165,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
@@ -162,7 +175,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int seg = 0;
-    for (int item = item_first; item <= item_last; ++item, ++seg) {
+    for (int w = 0; w < p.n_waves; ++w) {
+    CVB_WAVE_RANGE(w)
+    for (int litem = item_first; litem <= item_last; ++litem, ++seg) {
+      const int item = p.wave_item0[w] + litem;
       const int tg = item / (p.n_co_tiles * p.n_ci_tiles);
       const int t0 = tg * p.T;
       const int tcount = min(p.T, p.taps - t0);
@@ -180,7 +196,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t lbo = p.CM == 2 ? kWPatchStride : static_cast<uint32_t>(rb - ra) * 128;
         acc_lo[j] = static_cast<uint32_t>(ra) * 8 + ((lbo >> 4) << 16);
       }
-      const long long base = 1LL * item * p.total_tiles;
+      const long long base = 1LL * litem * p.total_tiles;
       const int tile_begin = static_cast<int>(max(u_begin, base) - base);
       const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
       // the epilogue must have drained the previous item's accumulators
@@ -216,13 +232,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (elect_one()) umma_commit(tfull);
       __syncwarp();
     }
+    }
   } else if (warp >= 4) {
     // --------------------------------- epilogue (once per item segment) -----------------------------------
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
     const int atom = row >> 6, r = row & 63;
     int seg = 0;
-    for (int item = item_first; item <= item_last; ++item, ++seg) {
+    for (int w = 0; w < p.n_waves; ++w) {
+    CVB_WAVE_RANGE(w)
+    for (int litem = item_first; litem <= item_last; ++litem, ++seg) {
+      const int item = p.wave_item0[w] + litem;
       const int co_tile = item % p.n_co_tiles;
       const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
       const int tg = item / (p.n_co_tiles * p.n_ci_tiles);
@@ -231,7 +251,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int units = tcount * p.CM;
       const int accs = (units + 1) >> 1;
       // this CTA's part number within the item = distance from the CTA that owns the item's first unit
-      const int part = static_cast<int>(blockIdx.x) - sk_owner(p.total_units, p.grid, 1LL * item * p.total_tiles);
+      const int part = static_cast<int>(blockIdx.x) - sk_owner(wave_units, p.wave_grid[w], 1LL * litem * p.total_tiles);
       mbar_wait(tfull, seg & 1);
       tc_fence_after();
       for (int j = 0; j < accs; ++j) {
@@ -264,7 +284,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty);
     }
+    }
   }
+#undef CVB_WAVE_RANGE
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -463,8 +485,10 @@ __global__ void __launch_bounds__(256) wgrad_partsum_kernel(float* __restrict__ 
     const int ci = static_cast<int>(t % p.cin_pad);
     const int tap = static_cast<int>(t / p.cin_pad);
     const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co / BN;
-    const long long u0 = 1LL * item * p.total_tiles;
-    const int parts = sk_owner(p.total_units, p.grid, u0 + p.total_tiles - 1) - sk_owner(p.total_units, p.grid, u0) + 1;
+    int w = 0;
+    while (w + 1 < p.n_waves && item >= p.wave_item0[w + 1]) ++w;
+    const long long wu = 1LL * p.wave_items[w] * p.total_tiles, u0 = 1LL * (item - p.wave_item0[w]) * p.total_tiles;
+    const int parts = sk_owner(wu, p.wave_grid[w], u0 + p.total_tiles - 1) - sk_owner(wu, p.wave_grid[w], u0) + 1;
     float4 acc = base[i];
     for (int s = 1; s < parts; ++s) {
       const float4 v = __ldcs(base + s * n4 + i);
@@ -584,6 +608,8 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
       if (parts > slots_rs) slots_rs = parts;
     }
     p.slots = slots_rs;
+    p.n_waves = 1;
+    p.wave_item0[0] = 0; p.wave_items[0] = p.items; p.wave_grid[0] = p.grid;
     plan->grid = p.grid;
     plan->smem = 1024 + kRsStages * kRsStageBytes + 256;
     plan->ws_bytes = 1LL * slots_rs * taps * cin_pad * cout_pad * 4;
@@ -605,25 +631,53 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
   p.items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
   p.total_units = 1LL * p.items * p.total_tiles;
-  // one CTA per SM, each an equal share of the flattened (item, tile) space; never more CTAs than units
-  p.grid = static_cast<int>(p.total_units < sm_count() ? p.total_units : sm_count());
-  {
-    // Lockstep: with a grid that is a multiple of the item count every item is cut at the same tile boundaries, so the
-    // CTAs of different items sweep the SAME pixel tiles at the same time and the x / dy tiles they share are fetched
-    // from HBM once and hit in L2 by the others. With the plain 148-way cut the items drift apart and the big layers
-    // re-read their operands 2.6-3.4x from HBM (ncu: 1.2 GB per launch against 354 MB on 256->128 at 180x240), which
-    // made them HBM-bound. Taken when it idles at most 7 % of the SMs. CVB_WGRAD_LOCKSTEP=0 disables (A/B).
-    const char* ls_env = getenv("CVB_WGRAD_LOCKSTEP");
-    const int S = p.items > 0 ? sm_count() / p.items : 0;
-    if (!(ls_env && atoi(ls_env) == 0) && p.items >= 2 && S >= 1 && S <= p.total_tiles &&
-        p.items * S * 100 >= sm_count() * 93)
-      p.grid = p.items * S;
+  // Work partition. Stream-K: the (item, pixel tile) space is flattened and cut into equal contiguous ranges, one per
+  // CTA. Lockstep: the grid of a partition is a MULTIPLE of its item count, so every item is cut at the same tile
+  // boundaries, the CTAs of different items sweep the SAME pixel tiles at the same time and the x / dy tiles they share
+  // are fetched from HBM once and hit in L2 by the others (with a plain 148-way cut the items drift apart and the big
+  // layers re-read their operands 2.6-7.8x from HBM: ncu, 1.2 GB per launch against 354 MB on 256->128 at 180x240).
+  // Waves: item counts that do not divide the SM count well (40, 80, 160 ...) are processed as successive lockstep
+  // partitions, e.g. 80 items = 74 items x 2 CTAs, then 6 items x 24 CTAs; per CTA the waves add up to an equal share.
+  // CVB_WGRAD_LOCKSTEP=0 falls back to one plain stream-K partition (A/B).
+  const int G = sm_count();
+  const char* ls_env = getenv("CVB_WGRAD_LOCKSTEP");
+  const bool lockstep = !(ls_env && atoi(ls_env) == 0);
+  p.n_waves = 0;
+  int remaining = p.items, off = 0;
+  while (remaining > 0) {
+    int take = remaining, grid_w;
+    const long long units = 1LL * remaining * p.total_tiles;
+    if (!lockstep || p.n_waves == kMaxWaves - 1) {
+      grid_w = static_cast<int>(units < G ? units : G);  // plain stream-K over everything that is left
+    } else if (remaining >= G) {
+      take = G;  // one whole item per CTA: no split-K at all
+      grid_w = G;
+    } else {
+      int S = G / remaining;
+      if (remaining * S * 100 < G * 93) {  // would idle more than 7 % of the SMs: split the items instead
+        S += 1;
+        take = G / S;
+      }
+      if (S > p.total_tiles) S = p.total_tiles;
+      grid_w = take * S;
+    }
+    p.wave_item0[p.n_waves] = off;
+    p.wave_items[p.n_waves] = take;
+    p.wave_grid[p.n_waves] = grid_w;
+    ++p.n_waves;
+    off += take;
+    remaining -= take;
   }
+  p.grid = 0;
   int slots = 1;
-  for (int item = 0; item < p.items; ++item) {
-    const long long u0 = 1LL * item * p.total_tiles;
-    const int parts = sk_owner(p.total_units, p.grid, u0 + p.total_tiles - 1) - sk_owner(p.total_units, p.grid, u0) + 1;
-    if (parts > slots) slots = parts;
+  for (int w = 0; w < p.n_waves; ++w) {
+    if (p.wave_grid[w] > p.grid) p.grid = p.wave_grid[w];
+    const long long wu = 1LL * p.wave_items[w] * p.total_tiles;
+    for (int li = 0; li < p.wave_items[w]; ++li) {
+      const long long u0 = 1LL * li * p.total_tiles;
+      const int parts = sk_owner(wu, p.wave_grid[w], u0 + p.total_tiles - 1) - sk_owner(wu, p.wave_grid[w], u0) + 1;
+      if (parts > slots) slots = parts;
+    }
   }
   p.slots = slots;
   plan->grid = p.grid;
