@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--width", type=int, default=480)
     ap.add_argument("--mode", default="train", choices=["train", "eval"],
                     help="eval: BASELINE config 5 (forward with running statistics + argmax + confusion matrix / mIoU)")
+    ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"],
+                    help="b200 = camvid_b200.optim.AdamW (fused drop-in, parity-tested against torch); torch = torch.optim.AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
@@ -188,6 +190,7 @@ def workload_config(args):
             "model_family": args.model, "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus,
             "height": args.height, "width": args.width, "classes": 12,
             "parallelism": f"dp{args.gpus}" if args.gpus > 1 else "single",
+            "optimizer": "camvid_b200.optim.AdamW (fused)" if getattr(args, "optimizer", "b200") == "b200" else "torch.optim.AdamW",
             "l2": "no flush needed: one step streams several GB of activations, far beyond the 126 MB L2"}
 
 
@@ -232,7 +235,11 @@ def run_b200(args):
     if world > 1:
         parallel.data_parallel(net)
     loss_fn = CrossEntropyLoss()
-    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0)  # as train.py:100 (fused=True: same speed)
+    if args.optimizer == "b200":
+        from camvid_b200.optim import AdamW
+    else:
+        AdamW = torch.optim.AdamW
+    opt = AdamW(net.parameters(), lr=5e-4, weight_decay=0)  # train.py:100
 
     g = torch.Generator().manual_seed(1 + rank)
     nbuf = 2

@@ -134,6 +134,24 @@ CVB_API int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, int 
                       int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer: torch.optim.AdamW(net.parameters(), lr, weight_decay).step(), train.py:100,133, for every
+ * parameter tensor in one launch (amsgrad = False, maximize = False; decoupled weight decay).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;        /* fp32, updated in place */
+  const float* grad;   /* fp32 */
+  float* exp_avg;      /* fp32 state, updated in place */
+  float* exp_avg_sq;   /* fp32 state, updated in place */
+  int64_t numel;
+} cvb_adamw_entry;
+/* Elements one CUDA block updates; the caller cuts every tensor into ceil(numel / this) chunks. */
+CVB_API int cvb_adamw_chunk_elems(void);
+/* table: DEVICE array of entries; chunks: DEVICE array of n_chunks (entry index, chunk index) int32 pairs.
+ * step = the 1-based step count of this update (bias corrections 1 - beta^step). */
+CVB_API int cvb_adamw_step(const cvb_adamw_entry* table, const int32_t* chunks, int n_chunks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (+ReLU) in training mode (nn.BatchNorm2d + nn.ReLU: models/unet.py:12-13, models/segnet.py:9-10).
  * ------------------------------------------------------------------------------------------------------------- */
 /* Per-channel partial sums of a view (used when the producer did not emit them): partials fp32 [rows][2][c]. */

@@ -46,6 +46,8 @@ SIGNATURES = {
     "cvb_conv_stat_rows": (_I, []),
     "cvb_conv3x3_fprop": (_I, [View, _P, _I, View, ctypes.POINTER(ConvEpilogue), _P]),
     "cvb_conv3x3_fprop_fuses_bwd_stats": (_I, [View, View, _I]),
+    "cvb_adamw_chunk_elems": (_I, []),
+    "cvb_adamw_step": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _L, _P]),
     "cvb_conv3x3_wgrad_workspace_bytes": (_L, [View, View, _I]),
     "cvb_conv3x3_wgrad": (_I, [View, View, _I, _P, _I, _I, _P, _L, _P]),
     "cvb_bn_stats": (_I, [View, _P, _I, _P]),

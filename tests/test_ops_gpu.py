@@ -437,3 +437,40 @@ def test_pack_weights_batch_equals_single_layer_packers(ops, cuda):
     torch.cuda.synchronize()
     for (w, df, dd, _, _), (sf, sd) in zip(entries, singles):
         assert torch.equal(df, sf) and torch.equal(dd, sd), tuple(w.shape)
+
+
+# ------------------------------------------------------------------------------------------- optimizer
+def test_fused_adamw_matches_torch_adamw(cuda):
+    """camvid_b200.optim.AdamW against torch.optim.AdamW (train.py:100) over several steps under OneCycleLR, which rewrites
+    lr and beta1 every step (train.py:102-104,134): parameters and both moments within fp32 rounding of each other;
+    state dicts interchangeable."""
+    import camvid_b200  # noqa: F401
+    from camvid_b200.optim import AdamW
+    torch.manual_seed(61)
+    shapes = [(64, 3, 3, 3), (64,), (128, 64, 3, 3), (12,), (5, 7), (100003,), (1,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.AdamW(ref_p, lr=5e-4, weight_decay=1e-2)
+    our = AdamW(our_p, lr=5e-4, weight_decay=1e-2)
+    rs = torch.optim.lr_scheduler.OneCycleLR(ref, max_lr=5e-4, steps_per_epoch=4, epochs=2)
+    os_ = torch.optim.lr_scheduler.OneCycleLR(our, max_lr=5e-4, steps_per_epoch=4, epochs=2)
+    for it in range(6):
+        flat = torch.randn(sum(p.numel() for p in ref_p), device=cuda)  # gradients = views of one flat buffer (engine)
+        off = 0
+        for a, b in zip(ref_p, our_p):
+            gslice = flat[off:off + a.numel()].view_as(a)
+            a.grad, b.grad = gslice.clone(), gslice
+            off += a.numel()
+        ref.step()
+        our.step()
+        rs.step()
+        os_.step()
+        for a, b in zip(ref_p, our_p):
+            torch.testing.assert_close(b, a, rtol=2e-6, atol=1e-7)
+    for a, b in zip(ref_p, our_p):
+        torch.testing.assert_close(our.state[b]["exp_avg"], ref.state[a]["exp_avg"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(our.state[b]["exp_avg_sq"], ref.state[a]["exp_avg_sq"], rtol=1e-5, atol=1e-7)
+        assert float(our.state[b]["step"]) == float(ref.state[a]["step"]) == 6.0
+    fresh = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in our_p], lr=5e-4)
+    fresh.load_state_dict(our.state_dict())  # same param_groups / state layout
+    assert fresh.state_dict()["state"][0]["exp_avg"].shape == shapes[0]
