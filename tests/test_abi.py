@@ -82,3 +82,20 @@ def test_loss_module_rejects_unsupported_options():
         CrossEntropyLoss(weight=torch.ones(12))
     with pytest.raises(ValueError):
         CrossEntropyLoss(label_smoothing=0.1)
+
+
+def test_wgrad_workspace_planner_is_host_only_and_consistent():
+    """cvb_conv3x3_wgrad_workspace_bytes runs the whole work-partition planner (stream-K ranges, lockstep waves) on the
+    host: it must answer without a GPU, and the workspace is a whole number of [taps][cin_pad][cout_pad] fp32 slots, at most
+    one per CTA (148 SMs assumed when no device is visible)."""
+    import ctypes
+    from camvid_b200 import _lib
+    lib = _lib.load()
+    for n, h, w, cin, cout in [(16, 360, 480, 64, 64), (16, 180, 240, 256, 128), (16, 90, 120, 512, 256),
+                               (16, 45, 60, 1024, 512), (16, 22, 30, 1024, 1024), (1, 11, 15, 512, 512), (2, 8, 8, 32, 64), (2, 40, 72, 64, 16)]:
+        x = _lib.View(ctypes.c_void_p(256), n, h, w, cin, h * w * cin, w * cin, cin)
+        dy = _lib.View(ctypes.c_void_p(256), n, h, w, cout, h * w * cout, w * cout, cout)
+        taps = 9 if cin >= 64 else 1
+        nbytes = lib.cvb_conv3x3_wgrad_workspace_bytes(x, dy, taps)
+        slot = taps * ((cin + 63) // 64 * 64) * ((cout + 63) // 64 * 64) * 4
+        assert nbytes > 0 and nbytes % slot == 0 and 1 <= nbytes // slot <= 148, (n, h, w, cin, cout, nbytes)
