@@ -897,7 +897,8 @@ conv_fprop_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 //     the MMA rows do useful work; taps that do not exist for a block are zero rows, fetched as an out-of-bounds TMA box).
 //   * B = a view of a ROW-PARITY patch: even image rows (dr = 0, 2) or odd ones (dr = -1, 1), 33 rows x 10 pixels, fetched
 //     once per 64-channel chunk through a 5-D tensor map (rows split into (pair, parity)); the view of (dr, dc) starts
-//     at patch row ((dr >> 1 or so) * 10 + dc + 1) with SBO = 10 pixels, like the taps of the halo kernel.
+//     at patch row k0 (0 for dr = 0 / -1, 1 for dr = 2 / +1), patch column dc + 1, i.e. 128-byte row k0 * 10 + dc + 1, with
+//     SBO = 10 pixels, like the taps of the halo kernel.
 //   * tile = 8 (w) x 64 (h) output pixels = 256 accumulator columns, double-buffered in TMEM (512 columns).
 //   * epilogue: a thread owns ONE (shift, channel) lane: BatchNorm statistics are two scalars per thread with no
 //     cross-lane work at all; stores are 2-byte, 32 lanes = 64 contiguous bytes of one pixel.
