@@ -190,7 +190,7 @@ class Plan:
     def __init__(self, module, n, h, w, device):
         self.module, self.n, self.h, self.w, self.device = module, n, h, w, device
         self.stat_rows = ops.stat_rows()
-        self.reduce_rows = 4 * ops.sm_count()
+        self.reduce_rows = int(os.environ.get("CVB_REDUCE_ROWS_PER_SM", "4")) * ops.sm_count()  # grid of the BN-backward reduction
         self.parts = torch.empty(max(self.stat_rows, self.reduce_rows), 2, 1024, device=device)
         self.blocks = []  # in forward order
         self.workspace = None
