@@ -269,14 +269,20 @@ def test_ignore_index_void(cvb, cuda):
     _check_grad_norms(net, o_grads)
 
 
-def test_optimizer_steps_follow_oracle(cvb, cuda):
+@pytest.mark.parametrize("fused_optimizer", [False, True])
+def test_optimizer_steps_follow_oracle(cvb, cuda, fused_optimizer):
     """Three AdamW steps (train.py:100,124-134): packed bf16 weights are refreshed from the fp32 parameters after
-    each optimizer.step(); the loss trajectory follows the fp32 oracle's."""
+    each optimizer.step(); the loss trajectory follows the fp32 oracle's -- with torch.optim.AdamW and with the fused
+    drop-in camvid_b200.optim.AdamW (the oracle side always steps torch's AdamW on the CPU)."""
     cutils, cnn = cvb
     torch.manual_seed(2)
     sd = {k: v.clone() for k, v in cutils.get_model("segnet", 3, 12).state_dict().items()}
     net = _build(cvb, "segnet", sd, cuda)
-    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0)
+    if fused_optimizer:
+        from camvid_b200.optim import AdamW
+    else:
+        AdamW = torch.optim.AdamW
+    opt = AdamW(net.parameters(), lr=5e-4, weight_decay=0)
     x, t = O.synth_batch(2, 64, 96, seed=9)
     # oracle side: functional model + the same optimizer on CPU tensors
     o_sd = {k: v.clone() for k, v in sd.items()}
