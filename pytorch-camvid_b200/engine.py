@@ -28,6 +28,7 @@ OVERLAP_WGRAD = True
 # Off by default: measured 1 % slower end to end -- the reduce pass it removes was already hidden under the side-stream
 # weight gradient, while the heavier epilogue lengthens the data gradient on the critical path (CVB_FUSE_BWD=1 enables).
 FUSE_BWD_STATS = os.environ.get("CVB_FUSE_BWD", "0") != "0"
+SERIALIZE_TENSOR_KERNELS = os.environ.get("CVB_SERIALIZE_TENSOR", "0") != "0"  # measured: see DESIGN.md knobs
 
 
 def narrow_channels(c):
@@ -159,6 +160,10 @@ class Block:
         fused = False
         if dx is not None:
             self._pack_d()
+            if p.wstream is not None and SERIALIZE_TENSOR_KERNELS:
+                # experiment: the data gradient waits for the previous block's weight gradient instead of sharing the
+                # SMs with its tail
+                torch.cuda.current_stream(p.device).wait_stream(p.wstream)
             if consumer is not None and FUSE_BWD_STATS:
                 if self._fuses is None:
                     self._fuses = (consumer.ce == consumer.cout_pad == dx.shape[3]
