@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 2
+#define CVB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CVB_API __attribute__((visibility("default")))
@@ -207,39 +207,49 @@ CVB_API int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream);
 CVB_API int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * nn.CrossEntropyLoss() forward + backward fused (train.py:105,130-131; eval.py:42,58): mean over counted pixels.
- * logits: NCHW fp32 [n,c,h,w] (the module boundary); target int64 [n,h,w].
- * loss_sum_count: double [2], ACCUMULATED into (caller zeroes): sum of -log p[target], number of counted pixels.
- *   A pixel is counted when target != ignore_index and 0 <= target < c (torch asserts on other values; here they
- *   are skipped).
- * dlogits (may be NULL): same layout as logits, receives (softmax - onehot) * gs, 0 for skipped pixels, where
- *   gs = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)  -- pass 1/count on the host when nothing is ignored,
- *   or a device scalar computed from the target when ignore_index is in use.
+ * Label tensors (targets / ground truth / predictions) are torch int64 at the reference API (`masks.cuda()`,
+ * train.py:127; `preds.argmax(dim=1)`, train.py:191) or the uint8 masks the device input stage keeps resident
+ * (cvb_input_stage_u8 below): every function that reads labels takes the element type.
  * ------------------------------------------------------------------------------------------------------------- */
-CVB_API int cvb_softmax_ce_nchw_f32(const float* logits, const int64_t* target, int n, int c, int h, int w,
-                            int64_t ignore_index, double* loss_sum_count, float* dlogits, float grad_scale,
-                            const float* grad_scale_dev, void* stream);
+typedef enum { CVB_LABEL_U8 = 1, CVB_LABEL_I64 = 8 } cvb_label_type; /* value = bytes per label */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * nn.CrossEntropyLoss() forward + backward fused (train.py:105,130-131; eval.py:42,58).
+ * logits: NCHW fp32 [n,c,h,w] (the module boundary); target [n,h,w] of `label_type`.
+ * A pixel is counted when target != ignore_index and 0 <= target < c.
+ * mean != 0 (reduction='mean', the reference's): loss = sum / counted, gradients scaled by grad_scale / counted --
+ *   the counted total is taken by a pre-pass over the target inside this call, so loss and gradient always agree
+ *   (ignore_index inside or outside [0,c)). mean == 0 (reduction='sum'): loss = sum, gradients scaled by grad_scale.
+ * scratch: double [4], ZEROED by the caller, private to this call (sum, counted, invalid labels, block ticket).
+ * loss_out: device float, written by the last block to finish. A label that is neither ignore_index nor in [0,c)
+ *   (torch raises a device-side assert) makes the loss NaN: it cannot pass unnoticed, and nothing is killed.
+ * dlogits (may be NULL): same layout as logits, receives (softmax - onehot) * scale, 0 for pixels not counted.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_softmax_ce_nchw_f32(const float* logits, const void* target, int label_type, int n, int c, int h, int w,
+                            int64_t ignore_index, int mean, double* scratch, float* loss_out, float* dlogits,
+                            float grad_scale, void* stream);
 /* Same on the model's internal NHWC bf16 logits view (first c channels); dlogits (ptr may be NULL) is an NHWC bf16
  * view whose channels >= c are written as zero. */
-CVB_API int cvb_softmax_ce_nhwc_bf16(cvb_view logits, int c, const int64_t* target, int64_t ignore_index,
-                             double* loss_sum_count, cvb_view dlogits, float grad_scale, const float* grad_scale_dev,
+CVB_API int cvb_softmax_ce_nhwc_bf16(cvb_view logits, int c, const void* target, int label_type, int64_t ignore_index,
+                             int mean, double* scratch, float* loss_out, cvb_view dlogits, float grad_scale,
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * preds.argmax(dim=1) + confusion matrix (train.py:191-194, utils.py:162-228, legacy/metrics.py:22-30).
  * cm: int64 [c][c], rows = ground truth, cols = prediction, ACCUMULATED into (caller zeroes).
- * cvb_confusion_matrix: pixels with gt == ignore_label are dropped (utils.py:178); with clamp_oob == 0 a pair with
- * either label outside [0,c) is dropped (sklearn `labels=range(C)`, legacy/metrics.py:29); with clamp_oob != 0 such
- * labels are counted in class c-1 (lets the caller keep an explicit out-of-range bucket, used to reproduce
- * np.histogram's per-array range handling in utils.py:183-187).
+ * cvb_confusion_matrix: pred and gt share `label_type`; pixels with gt == ignore_label are dropped (utils.py:178);
+ * with clamp_oob == 0 a pair with either label outside [0,c) is dropped (sklearn `labels=range(C)`,
+ * legacy/metrics.py:29); with clamp_oob != 0 such labels are counted in class c-1 (lets the caller keep an explicit
+ * out-of-range bucket, used to reproduce np.histogram's per-array range handling in utils.py:183-187).
  * ------------------------------------------------------------------------------------------------------------- */
-CVB_API int cvb_confusion_matrix(const int64_t* pred, const int64_t* gt, int64_t count, int c, int64_t ignore_label,
-                                 int clamp_oob, int64_t* cm, void* stream);
-/* Fused: first-max argmax over c channels of NCHW fp32 logits; optionally also writes pred (int64 [n,h,w]). */
-CVB_API int cvb_argmax_confusion_nchw_f32(const float* logits, const int64_t* gt, int n, int c, int h, int w,
+CVB_API int cvb_confusion_matrix(const void* pred, const void* gt, int label_type, int64_t count, int c,
+                                 int64_t ignore_label, int clamp_oob, int64_t* cm, void* stream);
+/* Fused: first-max argmax over c channels of NCHW fp32 logits; optionally also writes pred (int64 [n,h,w]).
+ * gt is of `label_type`. */
+CVB_API int cvb_argmax_confusion_nchw_f32(const float* logits, const void* gt, int label_type, int n, int c, int h, int w,
                                   int64_t* pred_or_null, int64_t* cm, void* stream);
-CVB_API int cvb_argmax_confusion_nhwc_bf16(cvb_view logits, int c, const int64_t* gt, int64_t* pred_or_null, int64_t* cm,
-                                   void* stream);
+CVB_API int cvb_argmax_confusion_nhwc_bf16(cvb_view logits, int c, const void* gt, int label_type, int64_t* pred_or_null,
+                                   int64_t* cm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Utilities

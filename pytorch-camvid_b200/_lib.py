@@ -64,15 +64,16 @@ SIGNATURES = {
     "cvb_pool_code_to_index": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "cvb_bilinear2x_fwd": (_I, [View, View, _P]),
     "cvb_bilinear2x_bwd": (_I, [View, View, _P]),
-    "cvb_softmax_ce_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P]),
-    "cvb_softmax_ce_nhwc_bf16": (_I, [View, _I, _P, _L, _P, View, _F, _P, _P]),
-    "cvb_confusion_matrix": (_I, [_P, _P, _L, _I, _L, _I, _P, _P]),
-    "cvb_argmax_confusion_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
-    "cvb_argmax_confusion_nhwc_bf16": (_I, [View, _I, _P, _P, _P, _P]),
+    "cvb_softmax_ce_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _L, _I, _P, _P, _P, _F, _P]),
+    "cvb_softmax_ce_nhwc_bf16": (_I, [View, _I, _P, _I, _L, _I, _P, _P, View, _F, _P]),
+    "cvb_confusion_matrix": (_I, [_P, _P, _I, _L, _I, _L, _I, _P, _P]),
+    "cvb_argmax_confusion_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "cvb_argmax_confusion_nhwc_bf16": (_I, [View, _I, _P, _I, _P, _P, _P]),
     "cvb_zero_view": (_I, [View, _P]),
 }
 
 _lib = None
+ABI_VERSION = 3  # CVB_ABI_VERSION of include/camvid_b200.h this binding was written against
 
 
 def build(verbose=False):
@@ -99,7 +100,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.cvb_abi_version() != 2:
+    if lib.cvb_abi_version() != ABI_VERSION:
         raise RuntimeError("libcamvid_b200.so ABI version mismatch")
     _lib = lib
     return lib

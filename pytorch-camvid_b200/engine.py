@@ -563,7 +563,8 @@ def net_forward_op(x: torch.Tensor, params: List[torch.Tensor], plan_handle: int
     the BatchNorm running statistics of the owning module, exactly like nn.BatchNorm2d."""
     plan = _plan_of(plan_handle)
     plan.generation += 1  # every forward overwrites the plan's activation buffers
-    return plan.forward(x, train)
+    with ops.on_device(x):  # kernels go to the CURRENT device's stream: make the tensor's device current
+        return plan.forward(x, train)
 
 
 @net_forward_op.register_fake
@@ -580,7 +581,8 @@ def net_backward_op(dlogits: torch.Tensor, plan_handle: int, generation: int) ->
     if generation != plan.generation:
         raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
                            "later forward of the same module and input shape (plans own one set of buffers)")
-    return plan.backward(dlogits.float().contiguous())
+    with ops.on_device(dlogits):  # autograd's worker thread of this device, but do not rely on it
+        return plan.backward(dlogits.float().contiguous())
 
 
 @net_backward_op.register_fake
@@ -626,7 +628,8 @@ def run_module(module, plan_cls, x):
         tracing = torch._C._get_tracing_state()
         torch._C._set_tracing_state(None)
         try:
-            plan = plan_cls(module, n, h, w, x.device)
+            with ops.on_device(x):
+                plan = plan_cls(module, n, h, w, x.device)
         finally:
             torch._C._set_tracing_state(tracing)
         plans[key] = plan

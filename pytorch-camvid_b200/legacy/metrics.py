@@ -24,15 +24,21 @@ class Metrics:
         if p.numel() != g.numel():
             raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]"
                              % (g.numel(), p.numel()))
-        cm = torch.zeros(self.class_num, self.class_num, dtype=torch.int64, device=p.device)
-        ops.confusion_matrix(p, g, self.class_num, cm)
+        if g.device != p.device:
+            g = g.to(p.device)
+        with ops.on_device(p):
+            cm = torch.zeros(self.class_num, self.class_num, dtype=torch.int64, device=p.device)
+            ops.confusion_matrix(p, g, self.class_num, cm)
         self._confusion_matrix += cm.cpu().numpy()
 
     def add_logits(self, logits, gts):
         """Extension: fused argmax(dim=1) + counting straight from fp32 NCHW logits (eval.py:61-64 in one kernel)."""
-        g = _to_cuda_i64(gts)
-        cm = torch.zeros(self.class_num, self.class_num, dtype=torch.int64, device=g.device)
-        ops.argmax_confusion_nchw(logits.detach().float().contiguous(), g, cm)
+        if not (torch.is_tensor(gts) and gts.is_cuda and gts.dtype == torch.uint8):  # uint8 device masks pass through
+            gts = _to_cuda_i64(gts)
+        g = gts.to(logits.device).contiguous()
+        with ops.on_device(logits):
+            cm = torch.zeros(self.class_num, self.class_num, dtype=torch.int64, device=g.device)
+            ops.argmax_confusion_nchw(logits.detach().float().contiguous(), g, cm)
         self._confusion_matrix += cm.cpu().numpy()
 
     def clear(self):

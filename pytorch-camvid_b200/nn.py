@@ -1,5 +1,8 @@
 """Drop-in for the loss the reference trains with: nn.CrossEntropyLoss() on fp32 NCHW logits and int64 targets
-(train.py:105,130-131; eval.py:42,58), backed by the fused softmax / loss / gradient kernel."""
+(train.py:105,130-131; eval.py:42,58), backed by the fused softmax / loss / gradient kernel. Stock
+torch.nn.CrossEntropyLoss works on the drop-in modules' logits too (they are ordinary autograd tensors); this one
+saves the separate log_softmax / nll_loss passes and also accepts the uint8 masks camvid_b200.data keeps on the device.
+"""
 import torch
 
 from . import ops
@@ -11,23 +14,18 @@ class _CEFunction(torch.autograd.Function):
     def forward(ctx, logits, target, ignore_index, reduction):
         if not (logits.is_cuda and logits.dim() == 4):
             raise RuntimeError("camvid_b200.nn.CrossEntropyLoss expects CUDA logits of shape [N,C,H,W]")
-        if target.dtype != torch.int64 or tuple(target.shape) != (logits.shape[0], logits.shape[2], logits.shape[3]):
-            raise RuntimeError("expected an int64 target of shape [N,H,W]")
-        lg = logits.detach().float().contiguous()
-        tg = target.contiguous()
-        acc = torch.zeros(2, dtype=torch.float64, device=lg.device)
-        need_grad = logits.requires_grad
-        dl = torch.empty_like(lg) if need_grad else None
-        if reduction == "mean":
-            if 0 <= ignore_index < lg.shape[1]:
-                inv = (1.0 / (tg != ignore_index).sum().to(torch.float32)).reshape(1)
-                ops.softmax_ce_nchw(lg, tg, ignore_index, acc, dl, 1.0, inv)
-            else:
-                ops.softmax_ce_nchw(lg, tg, ignore_index, acc, dl, 1.0 / tg.numel())
-            loss = (acc[0] / acc[1]).to(torch.float32)
-        else:
-            ops.softmax_ce_nchw(lg, tg, ignore_index, acc, dl, 1.0)
-            loss = acc[0].to(torch.float32)
+        if target.dtype not in (torch.int64, torch.uint8) or \
+                tuple(target.shape) != (logits.shape[0], logits.shape[2], logits.shape[3]):
+            raise RuntimeError("expected an int64 (or uint8) target of shape [N,H,W]")
+        if target.device != logits.device:
+            raise RuntimeError("logits and target are on different devices")
+        with ops.on_device(logits):
+            lg = logits.detach().float().contiguous()
+            tg = target.contiguous()
+            dl = torch.empty_like(lg) if logits.requires_grad else None
+            # the counted-pixel total behind reduction='mean' is taken on the device inside the call (pre-pass over
+            # the target), so the gradient scale always matches the loss denominator -- ignore_index in or out of range
+            loss = ops.softmax_ce_nchw(lg, tg, ignore_index, reduction == "mean", dl)
         ctx.dl = dl
         return loss
 
@@ -39,7 +37,8 @@ class _CEFunction(torch.autograd.Function):
 
 
 class CrossEntropyLoss(torch.nn.Module):
-    """Supports what the reference uses: no class weights, no label smoothing, reduction 'mean' (default) or 'sum'."""
+    """Supports what the reference uses: no class weights, no label smoothing, reduction 'mean' (default) or 'sum'.
+    A target that is neither ignore_index nor in [0, C) makes the loss NaN (torch raises a device-side assert)."""
 
     def __init__(self, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction='mean',
                  label_smoothing=0.0):

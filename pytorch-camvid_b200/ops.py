@@ -56,6 +56,15 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device(t):
+    """Context manager making t's GPU the current device: kernels are enqueued on the CURRENT device's current stream
+    and events / SM counts are taken from it, so every public entry point (module forward / backward, loss, metrics,
+    optimizer) wraps its work in this -- a module on cuda:1 works while cuda:0 is current."""
+    if not t.is_cuda:
+        raise RuntimeError("camvid_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    return torch.cuda.device(t.device)
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -300,32 +309,48 @@ def bilinear2x_bwd(dout, dx):
 
 
 # ---------------------------------------------------------------- loss / metric
-def softmax_ce_nchw(logits, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
+def label_type(t, name):
+    """cvb_label_type of a label tensor: int64 (the reference API) or uint8 (device-resident masks of the input stage)."""
+    if not (t.is_cuda and t.is_contiguous() and t.dtype in (torch.int64, torch.uint8)):
+        raise RuntimeError(f"{name}: expected a contiguous CUDA int64 or uint8 label tensor, got {t.dtype} on {t.device}")
+    return 8 if t.dtype == torch.int64 else 1
+
+
+def softmax_ce_nchw(logits, target, ignore_index, mean, dlogits, grad_scale=1.0):
+    """Fused CrossEntropyLoss forward (+ gradient when dlogits is given). Returns the loss as a device scalar (fp32);
+    NaN if a label is neither ignore_index nor in [0, C). Two launches for reduction='mean' (counted-pixel pre-pass)."""
     _f32(logits, "softmax_ce.logits")
     n, c, h, w = logits.shape
-    _call("softmax_ce_nchw_f32", 1, _nbytes(logits, target, dlogits), _lib.load().cvb_softmax_ce_nchw_f32,
-          _ptr(logits), _ptr(target), n, c, h, w, ignore_index, _ptr(loss_sum_count), _ptr(dlogits), grad_scale,
-          _ptr(grad_scale_dev), _stream())
+    scratch = torch.zeros(4, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    _call("softmax_ce_nchw_f32", 2 if mean else 1, _nbytes(logits, target, dlogits), _lib.load().cvb_softmax_ce_nchw_f32,
+          _ptr(logits), _ptr(target), label_type(target, "softmax_ce.target"), n, c, h, w, ignore_index,
+          1 if mean else 0, _ptr(scratch), _ptr(loss), _ptr(dlogits), grad_scale, _stream())
+    return loss
 
 
-def softmax_ce_nhwc(logits, c, target, ignore_index, loss_sum_count, dlogits, grad_scale, grad_scale_dev=None):
+def softmax_ce_nhwc(logits, c, target, ignore_index, mean, dlogits, grad_scale=1.0):
     px = logits.shape[0] * logits.shape[1] * logits.shape[2]
-    _call("softmax_ce_nhwc_bf16", 1, ("bytes", px * (c * 2 * (2 if dlogits is not None else 1) + 8.0)),
-          _lib.load().cvb_softmax_ce_nhwc_bf16, view(logits), c, _ptr(target), ignore_index, _ptr(loss_sum_count),
-          view(dlogits), grad_scale, _ptr(grad_scale_dev), _stream())
+    scratch = torch.zeros(4, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    _call("softmax_ce_nhwc_bf16", 2 if mean else 1,
+          ("bytes", px * (c * 2 * (2 if dlogits is not None else 1) + float(target.element_size()))),
+          _lib.load().cvb_softmax_ce_nhwc_bf16, view(logits), c, _ptr(target), label_type(target, "softmax_ce.target"),
+          ignore_index, 1 if mean else 0, _ptr(scratch), _ptr(loss), view(dlogits), grad_scale, _stream())
+    return loss
 
 
 NO_IGNORE = -(2 ** 62)
 
 
 def confusion_matrix(pred, gt, c, cm, ignore_label=NO_IGNORE, clamp_oob=False):
-    """cm[gt, pred] += counts over int64 label tensors (any shape, same numel)."""
-    for t, nm in ((pred, "pred"), (gt, "gt")):
-        if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
-            raise RuntimeError(f"confusion_matrix.{nm}: expected a contiguous CUDA int64 tensor")
+    """cm[gt, pred] += counts over label tensors (any shape, same numel, same dtype: int64 or uint8)."""
+    lt = label_type(pred, "confusion_matrix.pred")
+    if label_type(gt, "confusion_matrix.gt") != lt:
+        raise RuntimeError("confusion_matrix: pred and gt must have the same dtype")
     if pred.numel() != gt.numel():
         raise RuntimeError("confusion_matrix: pred and gt sizes differ")
-    _call("confusion_matrix", 1, _nbytes(pred, gt), _lib.load().cvb_confusion_matrix, _ptr(pred), _ptr(gt),
+    _call("confusion_matrix", 1, _nbytes(pred, gt), _lib.load().cvb_confusion_matrix, _ptr(pred), _ptr(gt), lt,
           pred.numel(), c, ignore_label, 1 if clamp_oob else 0, _ptr(cm), _stream())
     return cm
 
@@ -334,12 +359,13 @@ def argmax_confusion_nchw(logits, gt, cm, pred=None):
     _f32(logits, "argmax_confusion.logits")
     n, c, h, w = logits.shape
     _call("argmax_confusion_nchw_f32", 1, _nbytes(logits, gt, pred), _lib.load().cvb_argmax_confusion_nchw_f32,
-          _ptr(logits), _ptr(gt), n, c, h, w, _ptr(pred), _ptr(cm), _stream())
+          _ptr(logits), _ptr(gt), label_type(gt, "argmax_confusion.gt"), n, c, h, w, _ptr(pred), _ptr(cm), _stream())
     return cm
 
 
 def argmax_confusion_nhwc(logits, c, gt, cm, pred=None):
     px = logits.shape[0] * logits.shape[1] * logits.shape[2]
-    _call("argmax_confusion_nhwc_bf16", 1, ("bytes", px * (c * 2 + 8.0 + (8.0 if pred is not None else 0.0))),
-          _lib.load().cvb_argmax_confusion_nhwc_bf16, view(logits), c, _ptr(gt), _ptr(pred), _ptr(cm), _stream())
+    _call("argmax_confusion_nhwc_bf16", 1, ("bytes", px * (c * 2 + float(gt.element_size()) + (8.0 if pred is not None else 0.0))),
+          _lib.load().cvb_argmax_confusion_nhwc_bf16, view(logits), c, _ptr(gt), label_type(gt, "argmax_confusion.gt"),
+          _ptr(pred), _ptr(cm), _stream())
     return cm

@@ -75,4 +75,9 @@ class AdamW(torch.optim.Optimizer):
                               _lib.load().cvb_adamw_step, ctypes.c_void_p(table.data_ptr()),
                               ctypes.c_void_p(chunks.data_ptr()), chunks.shape[0], float(group["lr"]), float(beta1),
                               float(beta2), float(group["eps"]), float(group["weight_decay"]), step, ops._stream())
+                # The kernel wrote the parameters through raw pointers: tell torch, exactly as an in-place op would.
+                # The execution plans key their packed bf16 GEMM operands on (data_ptr, _version) of the fp32 weight
+                # (engine.Block._weight_key) and re-pack when it moves; without this they would keep convolving with
+                # the initial weights.
+                torch.autograd.graph.increment_version(params)
         return loss

@@ -45,8 +45,11 @@ def _areas(pred, label, num_classes, ignore_index):
     the last bin is closed, so the value C is counted in class C-1."""
     C = num_classes
     ext = C + 2  # classes 0..C-1, the value C (np.histogram's closed last bin), everything else
-    cm = torch.zeros(ext, ext, dtype=torch.int64, device=pred.device)
-    ops.confusion_matrix(pred, label, ext, cm, ignore_label=ignore_index, clamp_oob=True)
+    if label.device != pred.device:
+        label = label.to(pred.device)
+    with ops.on_device(pred):
+        cm = torch.zeros(ext, ext, dtype=torch.int64, device=pred.device)
+        ops.confusion_matrix(pred, label, ext, cm, ignore_label=ignore_index, clamp_oob=True)
     cm = cm.cpu().numpy().astype(np.float64)
     inter = np.diag(cm)[:C].copy()
     inter[C - 1] += cm[C, C]

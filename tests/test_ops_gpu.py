@@ -368,33 +368,57 @@ def test_bilinear2x(ops, cuda, n, h, w, c):
 # ------------------------------------------------------------------------------------------- loss / metric
 @pytest.mark.parametrize("hw", [(17, 23), (16, 24)])  # generic kernel / four-pixel vectorised 12-class kernel
 @pytest.mark.parametrize("ignore", [-100, 11])
-def test_softmax_ce(ops, cuda, ignore, hw):
+@pytest.mark.parametrize("labels", ["int64", "uint8"])
+def test_softmax_ce(ops, cuda, ignore, hw, labels):
     torch.manual_seed(25)
     n, c, (h, w) = 3, 12, hw
     logits = F.relu(torch.randn(n, c, h, w) * 2).to(cuda).requires_grad_(True)
     target = torch.randint(0, c, (n, h, w)).to(cuda)
+    if ignore == -100:
+        target[0, :3] = -100 if labels == "int64" else 11  # ignored pixels with the default index too (int64 only)
     ref = F.cross_entropy(logits, target, ignore_index=ignore)
     (dref,) = torch.autograd.grad(ref, logits)
-    acc = torch.zeros(2, dtype=torch.float64, device=cuda)
+    tg = target if labels == "int64" else target.to(torch.uint8)
     dl = torch.empty_like(logits)
-    cnt = (target != ignore).sum()
-    inv = (1.0 / cnt.float()).reshape(1)
-    ops.softmax_ce_nchw(logits.detach(), target, ignore, acc, dl, 1.0, inv)
-    assert acc[1].item() == cnt.item()
-    assert abs(acc[0].item() / acc[1].item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
-    assert rel_err(dl, dref) < 1e-5
+    loss = ops.softmax_ce_nchw(logits.detach(), tg, ignore, True, dl)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert rel_err(dl, dref) < 1e-5  # gradient scale = 1 / counted pixels, whatever ignore_index is
+    # reduction='sum'
+    ref_s = F.cross_entropy(logits, target, ignore_index=ignore, reduction="sum")
+    (dref_s,) = torch.autograd.grad(ref_s, logits)
+    loss_s = ops.softmax_ce_nchw(logits.detach(), tg, ignore, False, dl)
+    assert abs(loss_s.item() - ref_s.item()) < 1e-5 * abs(ref_s.item())
+    assert rel_err(dl, dref_s) < 1e-5
     # NHWC bf16 variant (model-internal logits, 64-channel padded gradient)
     lg = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda)
     lg[..., :c] = to_nhwc_bf16(logits.detach())
     lq = to_nchw_f32(lg[..., :c]).requires_grad_(True)
     ref2 = F.cross_entropy(lq, target, ignore_index=ignore)
     (dref2,) = torch.autograd.grad(ref2, lq)
-    acc.zero_()
     dl2 = torch.full((n, h, w, 64), 1.0, dtype=torch.bfloat16, device=cuda)
-    ops.softmax_ce_nhwc(lg, c, target, ignore, acc, dl2, 1.0, inv)
-    assert abs(acc[0].item() / acc[1].item() - ref2.item()) < 1e-5 * max(1.0, abs(ref2.item()))
+    loss2 = ops.softmax_ce_nhwc(lg, c, tg, ignore, True, dl2)
+    assert abs(loss2.item() - ref2.item()) < 1e-5 * max(1.0, abs(ref2.item()))
     assert rel_err(to_nchw_f32(dl2[..., :c]), dref2) < 4e-3
     assert torch.count_nonzero(dl2[..., c:]) == 0
+
+
+def test_softmax_ce_flags_out_of_range_labels_and_all_ignored(ops, cuda):
+    """torch raises a device-side assert on a label that is neither ignore_index nor in [0, C); across the C ABI the
+    loss is poisoned with NaN instead (nothing is killed, nothing passes silently). All pixels ignored: 0/0 = NaN and
+    a zero gradient, like torch."""
+    torch.manual_seed(27)
+    n, c, h, w = 2, 12, 16, 24
+    logits = torch.randn(n, c, h, w, device=cuda)
+    target = torch.randint(0, c, (n, h, w), device=cuda)
+    dl = torch.empty_like(logits)
+    assert torch.isfinite(ops.softmax_ce_nchw(logits, target, -100, True, dl))
+    bad = target.clone()
+    bad[1, 3, 5] = 255  # settings.IGNORE_LABEL (conf/settings.py:25) without telling the loss
+    assert torch.isnan(ops.softmax_ce_nchw(logits, bad, -100, True, dl))
+    assert torch.isfinite(ops.softmax_ce_nchw(logits, bad, 255, True, dl))
+    allig = torch.full_like(target, 7)
+    assert torch.isnan(ops.softmax_ce_nchw(logits, allig, 7, True, dl))
+    assert torch.count_nonzero(dl) == 0
 
 
 @pytest.mark.parametrize("hw", [(33, 47), (32, 44)])  # generic kernels / vectorised 12-class argmax kernel
@@ -419,6 +443,13 @@ def test_confusion_matrix_bit_exact(ops, cuda, hw):
     pred2 = torch.empty_like(pred)
     ops.argmax_confusion_nhwc(lg, c, gt, cm, pred2)
     assert torch.equal(pred2, to_nchw_f32(lg[..., :c]).argmax(1))
+    # uint8 ground truth (device-resident masks of the input stage): same counts
+    cm.zero_()
+    ops.argmax_confusion_nchw(logits, gt.to(torch.uint8), cm)
+    assert torch.equal(cm, cm_ref)
+    cm.zero_()
+    ops.confusion_matrix(pred_ref.to(torch.uint8), gt.to(torch.uint8), c, cm)
+    assert torch.equal(cm, cm_ref)
 
 
 def test_pack_weights_batch_equals_single_layer_packers(ops, cuda):

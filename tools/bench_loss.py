@@ -14,7 +14,6 @@ dev = torch.device("cuda")
 logits = torch.relu(torch.randn(n, c, h, w, device=dev))
 target = torch.randint(0, c, (n, h, w), device=dev)
 dl = torch.empty_like(logits)
-acc = torch.zeros(2, dtype=torch.float64, device=dev)
 cm = torch.zeros(c, c, dtype=torch.int64, device=dev)
 pred = torch.empty(n, h, w, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -37,8 +36,10 @@ def timeit(name, fn, nbytes):
     print(f"{name:34s} {med * 1e3:8.1f} us  {nbytes / med / 1e6:8.1f} GB/s  ({nbytes / 1e6:.0f} MB)")
 
 
-timeit("softmax_ce fwd+bwd (fp32 NCHW)", lambda: ops.softmax_ce_nchw(logits, target, -100, acc, dl, 1.0 / px), px * (48 + 8 + 48))
-timeit("softmax_ce fwd only", lambda: ops.softmax_ce_nchw(logits, target, -100, acc, None, 1.0), px * (48 + 8))
+timeit("softmax_ce fwd+bwd (fp32 NCHW)", lambda: ops.softmax_ce_nchw(logits, target, -100, True, dl), px * (48 + 8 + 8 + 48))
+timeit("softmax_ce fwd only", lambda: ops.softmax_ce_nchw(logits, target, -100, True, None), px * (48 + 8 + 8))
+t8 = target.to(torch.uint8)
+timeit("softmax_ce fwd+bwd, uint8 labels", lambda: ops.softmax_ce_nchw(logits, t8, -100, True, dl), px * (48 + 1 + 1 + 48))
 timeit("argmax + confusion (fp32 NCHW)", lambda: ops.argmax_confusion_nchw(logits, target, cm), px * (48 + 8))
 timeit("argmax + confusion + pred", lambda: ops.argmax_confusion_nchw(logits, target, cm, pred), px * (48 + 8 + 8))
 timeit("confusion matrix (int64 labels)", lambda: ops.confusion_matrix(pred, target, c, cm), px * 16)
