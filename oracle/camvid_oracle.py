@@ -129,6 +129,24 @@ def _cbr_bf16(x, sd, conv, bn, train, momentum=0.1, eps=1e-5):
     return _StoreBF16.apply(a, False, True)  # gradients from several consumers are summed, then stored in bf16
 
 
+def block_step(x, w, bias, gamma, beta, dout, need_dx=True, storage="fp32", eps=1e-5):
+    """One conv3x3(pad 1, bias) -> BatchNorm2d(batch statistics) -> ReLU block (models/unet.py:5-17,
+    models/segnet.py:5-17) forward + backward on its own: returns (a, dx or None, dw, dgamma, dbeta) for the output
+    gradient `dout`. storage="bf16": the bf16 storage model of the block (see above). Used by the teacher-forced block
+    tests at the BASELINE geometries, where running the whole network through autograd on the CPU is too large."""
+    xr = x.detach().clone().requires_grad_(need_dx)
+    ps = [t.detach().clone().requires_grad_(True) for t in (w, gamma, beta)]
+    if storage == "fp32":
+        y = F.conv2d(xr, ps[0], bias, padding=1)
+        a = F.relu(F.batch_norm(y, None, None, ps[1], ps[2], True, 0.1, eps))
+        gout = dout
+    else:
+        a, _, _ = _BlockBF16.apply(xr, ps[0], ps[1], ps[2], eps)
+        gout = _r(dout)
+    g = torch.autograd.grad(a, ps + ([xr] if need_dx else []), grad_outputs=gout)
+    return a.detach(), (g[3] if need_dx else None), g[0], g[1], g[2]
+
+
 def _held(x, fwd=True, bwd=True):
     """Marks a tensor (and its gradient) as written to a bf16 buffer; identity under fp32 storage."""
     return x if STORAGE == "fp32" else _StoreBF16.apply(x, fwd, bwd)
