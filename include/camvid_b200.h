@@ -252,6 +252,21 @@ CVB_API int cvb_argmax_confusion_nhwc_bf16(cvb_view logits, int c, const void* g
                                    int64_t* cm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Device input stage: transforms.ToTensor + transforms.Normalize (transforms.py:485-538) and the
+ * mask's `.long()` (transforms.py:503), moved behind the host->device copy of train.py:126-127 so that the uint8
+ * image and mask cross PCIe instead of fp32 / int64 tensors (5x fewer bytes).
+ *   img_u8   DEVICE uint8 [n,h,w,c], HWC as cv2.imread / the dataset yield it (dataset/camvid.py:161-173), c <= 4
+ *   out_nchw DEVICE fp32 [n,c,h,w] = ((float(u8) / 255) - mean[c]) / std[c], each operation rounded to fp32 exactly as
+ *            torch does it (IEEE division, subtraction, IEEE division: bit-exact against the reference transforms)
+ *   mean_host / std_host: HOST arrays of c floats (conf/settings.py:8-9 for CamVid BGR)
+ *   mask_u8  DEVICE uint8 [n,h,w]; mask_i64 DEVICE int64 [n,h,w] or NULL (the loss and metric kernels read uint8
+ *            labels directly: cvb_label_type). img_u8 / out_nchw may both be NULL to convert a mask only.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_input_stage_u8(const uint8_t* img_u8, int n, int h, int w, int c, const float* mean_host,
+                               const float* std_host, float* out_nchw, const uint8_t* mask_u8, int64_t* mask_i64,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Utilities
  * ------------------------------------------------------------------------------------------------------------- */
 /* Zero-fills a bf16 view (pad rows of concat buffers). */

@@ -254,6 +254,21 @@ def _train_step(name, sd, x, target, ignore_index):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# input stage: transforms.ToTensor + transforms.Normalize (transforms.py:485-538)
+# ----------------------------------------------------------------------------------------------------------------
+def to_tensor_normalize(img_u8_hwc, mask_u8, mean, std):
+    """img uint8 [N,H,W,C] (HWC, cv2) -> fp32 [N,C,H,W]; mask uint8 [N,H,W] -> int64. numpy fp32, operation by
+    operation as the reference: `img.float() / 255.0` (transforms.py:500-501: IEEE division), then
+    `img.sub_(mean[:, None, None]).div_(std[:, None, None])` (transforms.py:536-538)."""
+    x = np.asarray(img_u8_hwc).transpose(0, 3, 1, 2).astype(np.float32)
+    x = x / np.float32(255.0)
+    m = np.asarray(mean, dtype=np.float32).reshape(1, -1, 1, 1)
+    s = np.asarray(std, dtype=np.float32).reshape(1, -1, 1, 1)
+    x = (x - m).astype(np.float32) / s
+    return x.astype(np.float32), np.asarray(mask_u8).astype(np.int64)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # metrics
 # ----------------------------------------------------------------------------------------------------------------
 def _hist(values, num_classes):

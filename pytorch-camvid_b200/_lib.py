@@ -69,6 +69,7 @@ SIGNATURES = {
     "cvb_confusion_matrix": (_I, [_P, _P, _I, _L, _I, _L, _I, _P, _P]),
     "cvb_argmax_confusion_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_argmax_confusion_nhwc_bf16": (_I, [View, _I, _P, _I, _P, _P, _P]),
+    "cvb_input_stage_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cvb_zero_view": (_I, [View, _P]),
 }
 

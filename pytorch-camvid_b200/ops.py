@@ -129,6 +129,33 @@ def zero_view(t):
     return t
 
 
+def input_stage_u8(img_u8, mean, std, out, mask_u8=None, mask_i64=None):
+    """transforms.ToTensor + transforms.Normalize (transforms.py:485-538) on the device: img_u8 uint8 [N,H,W,C] (HWC, as
+    cv2 yields it) -> out fp32 [N,C,H,W], bit-exact with the reference transforms; mask_u8 uint8 [N,H,W] -> mask_i64
+    (optional). Either half may be None."""
+    if img_u8 is not None:
+        if not (img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.is_contiguous()):
+            raise RuntimeError("input_stage_u8: expected a contiguous CUDA uint8 [N,H,W,C] image batch")
+        n, h, w, c = img_u8.shape
+        _f32(out, "input_stage_u8.out")
+        if tuple(out.shape) != (n, c, h, w) or len(mean) != c or len(std) != c:
+            raise RuntimeError("input_stage_u8: out must be [N,C,H,W] and mean / std must have C entries")
+    else:
+        n, h, w = mask_u8.shape
+        c = 0
+    if mask_i64 is not None:
+        if not (mask_u8 is not None and mask_u8.is_cuda and mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
+                and mask_i64.is_cuda and mask_i64.dtype == torch.int64 and mask_i64.is_contiguous()
+                and tuple(mask_u8.shape) == (n, h, w) == tuple(mask_i64.shape)):
+            raise RuntimeError("input_stage_u8: masks must be contiguous CUDA uint8 / int64 [N,H,W] tensors")
+    fl = ctypes.c_float * max(c, 1)
+    _call("input_stage_u8", 1, _nbytes(img_u8, out, mask_u8 if mask_i64 is not None else None, mask_i64),
+          _lib.load().cvb_input_stage_u8, _ptr(img_u8), n, h, w, c, fl(*[float(v) for v in mean][:c]) if c else None,
+          fl(*[float(v) for v in std][:c]) if c else None, _ptr(out), _ptr(mask_u8 if mask_i64 is not None else None),
+          _ptr(mask_i64), _stream())
+    return out, mask_i64
+
+
 # ---------------------------------------------------------------- convolution
 def pack_weights_fprop(w, taps, cout_pad, cin_pad, out=None):
     """OIHW fp32 -> bf16 [cout_pad, taps*cin_pad] GEMM-B matrix."""

@@ -122,8 +122,36 @@ def loss_fixture():
     print("loss fixtures written")
 
 
+def input_stage_fixture():
+    """transforms.ToTensor + transforms.Normalize (transforms.py:485-538) with the CamVid statistics
+    (conf/settings.py:8-9) on uint8 HWC images that contain every byte value in every channel, plus the mask's
+    .long(): the reference output the device input stage (cvb_input_stage_u8) must reproduce bit for bit."""
+    import transforms as ref_transforms  # reference
+    from conf import settings  # reference
+    rng = np.random.default_rng(11)
+    out = {"mean": np.array(settings.MEAN), "std": np.array(settings.STD)}
+    for tag, (n, h, w) in (("vec", (2, 24, 32)), ("odd", (3, 9, 11))):  # h*w % 4 == 0 / generic kernel
+        img = rng.integers(0, 256, (n, h, w, 3)).astype(np.uint8)
+        img.reshape(-1, 3)[:256] = np.stack([np.arange(256), np.arange(255, -1, -1), np.roll(np.arange(256), 97)], 1)
+        mask = rng.integers(0, 12, (n, h, w)).astype(np.uint8)
+        chain = ref_transforms.Compose([ref_transforms.ToTensor(), ref_transforms.Normalize(settings.MEAN, settings.STD)])
+        res = [chain(img[i].copy(), mask[i].copy()) for i in range(n)]
+        out[f"{tag}/img"], out[f"{tag}/mask"] = img, mask
+        out[f"{tag}/out"] = torch.stack([r[0] for r in res]).numpy()
+        out[f"{tag}/mask_out"] = torch.stack([r[1] for r in res]).numpy()
+        assert out[f"{tag}/out"].dtype == np.float32 and out[f"{tag}/mask_out"].dtype == np.int64
+    np.savez_compressed(os.path.join(OUT, "input_stage.npz"), **out)
+    print("input stage fixtures written")
+
+
 if __name__ == "__main__":
-    model_fixture("unet", 2, 40, 72)
-    model_fixture("segnet", 2, 40, 72)
-    metric_fixture()
-    loss_fixture()
+    only = sys.argv[1:]
+    if not only or "models" in only:
+        model_fixture("unet", 2, 40, 72)
+        model_fixture("segnet", 2, 40, 72)
+    if not only or "metrics" in only:
+        metric_fixture()
+    if not only or "loss" in only:
+        loss_fixture()
+    if not only or "input_stage" in only:
+        input_stage_fixture()

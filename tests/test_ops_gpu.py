@@ -505,3 +505,65 @@ def test_fused_adamw_matches_torch_adamw(cuda):
     fresh = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in our_p], lr=5e-4)
     fresh.load_state_dict(our.state_dict())  # same param_groups / state layout
     assert fresh.state_dict()["state"][0]["exp_avg"].shape == shapes[0]
+
+
+# ------------------------------------------------------------------------------------------- input stage
+def test_input_stage_bit_exact_with_reference_transforms(ops, cuda):
+    """cvb_input_stage_u8 against the fixture produced by the reference's transforms.ToTensor + transforms.Normalize
+    (transforms.py:485-538; tests/golden/make_golden.py) -- every byte value in every channel -- and against the oracle
+    restatement on a CamVid-sized batch: bit-exact, image and mask."""
+    import os
+    import numpy as np
+    from oracle import camvid_oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_stage.npz"))
+    mean, std = tuple(g["mean"]), tuple(g["std"])
+    for tag in ("vec", "odd"):
+        img, mask = torch.from_numpy(g[f"{tag}/img"]).to(cuda), torch.from_numpy(g[f"{tag}/mask"]).to(cuda)
+        n, h, w, c = img.shape
+        out = torch.full((n, c, h, w), float("nan"), device=cuda)
+        m64 = torch.full((n, h, w), -1, dtype=torch.int64, device=cuda)
+        ops.input_stage_u8(img, mean, std, out, mask, m64)
+        assert torch.equal(out.cpu(), torch.from_numpy(g[f"{tag}/out"])), tag
+        assert torch.equal(m64.cpu(), torch.from_numpy(g[f"{tag}/mask_out"])), tag
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (4, 360, 480, 3)).astype(np.uint8)
+    mask = rng.integers(0, 12, (4, 360, 480)).astype(np.uint8)
+    ref, ref_m = O.to_tensor_normalize(img, mask, mean, std)
+    out = torch.empty(4, 3, 360, 480, device=cuda)
+    m64 = torch.empty(4, 360, 480, dtype=torch.int64, device=cuda)
+    ops.input_stage_u8(torch.from_numpy(img).to(cuda), mean, std, out, torch.from_numpy(mask).to(cuda), m64)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref)) and torch.equal(m64.cpu(), torch.from_numpy(ref_m))
+    # mask only
+    m64.fill_(-1)
+    ops.input_stage_u8(None, (), (), None, torch.from_numpy(mask).to(cuda), m64)
+    assert torch.equal(m64.cpu(), torch.from_numpy(ref_m))
+
+
+@pytest.mark.parametrize("mask_dtype", [torch.int64, torch.uint8])
+def test_device_prefetcher(cuda, mask_dtype):
+    """camvid_b200.data.DevicePrefetcher over a loader of uint8 HWC batches (ragged last batch, pageable memory): every
+    yielded batch equals the oracle's ToTensor + Normalize of the matching host batch, in order; h2d byte accounting;
+    the reference's own fp32 / int64 batch format passes through unchanged."""
+    import numpy as np
+    import camvid_b200  # noqa: F401
+    from camvid_b200 import data
+    from oracle import camvid_oracle as O
+    rng = np.random.default_rng(5)
+    sizes = [4, 4, 4, 4, 3]
+    batches = [(rng.integers(0, 256, (b, 36, 48, 3)).astype(np.uint8), rng.integers(0, 12, (b, 36, 48)).astype(np.uint8))
+               for b in sizes]
+    pf = data.DevicePrefetcher(batches, cuda, mask_dtype=mask_dtype)
+    seen = 0
+    for (img, mask), (x, m) in zip(batches, pf):
+        ref, ref_m = O.to_tensor_normalize(img, mask, data.CAMVID_MEAN, data.CAMVID_STD)
+        assert x.dtype == torch.float32 and m.dtype == mask_dtype and x.is_cuda and m.is_cuda
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(x.cpu(), torch.from_numpy(ref)), seen
+        assert torch.equal(m.cpu().to(torch.int64), torch.from_numpy(ref_m)), seen
+        seen += 1
+    assert seen == len(sizes)
+    assert pf.h2d_bytes == sum(i.size + m.size for i, m in batches)
+    if mask_dtype == torch.int64:
+        ref_batches = [(torch.randn(2, 3, 8, 12), torch.randint(0, 12, (2, 8, 12))) for _ in range(3)]
+        for (img, mask), (x, m) in zip(ref_batches, data.DevicePrefetcher(ref_batches, cuda)):
+            assert torch.equal(x.cpu(), img) and torch.equal(m.cpu(), mask)
