@@ -9,16 +9,20 @@ N > 1 is launched by torchrun (one rank per GPU); per-GPU batch is fixed (weak s
 over NCCL in buckets on a side stream. Rank 0 prints ONE JSON line.
 
   value         images/s, whole job, inputs resident in HBM, CUDA-event time over exactly K steps, max over ranks
-  e2e           the same through the public API with HOST inputs: per step a pinned host->device copy of the fp32 NCHW
-                images + int64 masks and a device->host read of the loss
+  e2e           the same through the public API with HOST inputs: camvid_b200.data.DevicePrefetcher copies each step's uint8
+                HWC images + uint8 masks (what cv2 / the dataset yield) from pageable host memory through its pinned ring
+                on a side stream and runs ToTensor + Normalize on the device; the loss is read back every step
   roofline      the dominant kernel family (cvb_conv3x3_fprop: every forward conv and every data-gradient conv):
                 algorithmic FLOPs of its launches / their CUDA-event durations, measured on K further steps of the same
                 workload with an event pair around every C-ABI call (kept out of `value` so the events cannot perturb it)
   kernels       the same arithmetic for every other kernel family (HBM-bound ones in GB/s)
-  cpu_baseline  the fp32 oracle port of the reference path timed on this box's host cores (bounded sample)
+  cpu_baseline  the reference's own training step (oracle/_ref: its unmodified modules, staged by oracle/make_ref.py)
+                timed on this box's host cores on a bounded sample; the oracle port if oracle/_ref is absent
+  dp_check      N > 1: gradients of one batch through the bucketed NCCL reducer against the all-reduced mean of the
+                rank-local gradients, and the spread of the parameters over the ranks after the timed steps
 
-`--impl reference` times the reference's own CPU path (the oracle port: the reference is Python over torch and its
-tree does not travel to the GPU box) with all host threads, same metric / unit.
+`--impl reference` times the reference's own CPU path (oracle/_ref, else the oracle port) with all host threads on
+BASELINE.md section 5's fixed sample (batch 2 of the same geometry), same metric / unit.
 """
 import argparse
 import json
@@ -124,9 +128,14 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
 def cpu_reference_run(model, sample_batch, h, w, steps, warmup, threads=None):
-    """The reference's training step (get_model + CrossEntropyLoss + AdamW, fp32, train.py:100-134) restated by the
-    oracle, on the host cores. Returns (images/s, seconds per step, threads)."""
+    """The reference's training step (get_model + CrossEntropyLoss + AdamW, fp32, train.py:100-134) on the host cores:
+    the reference's own modules when oracle/_ref is staged (kind "reference"), else the oracle port (kind "port").
+    Returns (images/s, seconds per step, threads, kind)."""
     import torch
+    from oracle import ref_runner
+    if ref_runner.available():
+        v, sec, thr, _ = ref_runner.train_steps(model, sample_batch, h, w, steps, warmup, threads)
+        return v, sec, thr, "reference"
     from oracle import camvid_oracle as O
     import camvid_b200  # noqa: F401  (module tree only: parameter names / shapes / default init; never run on CPU)
     from camvid_b200.utils import get_model
@@ -153,7 +162,7 @@ def cpu_reference_run(model, sample_batch, h, w, steps, warmup, threads=None):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return sample_batch / sec, sec, torch.get_num_threads()
+    return sample_batch / sec, sec, torch.get_num_threads(), "port"
 
 
 def run_reference(args):
@@ -163,22 +172,22 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: probe one step at batch 1, then pick the sample batch that keeps the whole run near 3 minutes
-    _, probe, _ = cpu_reference_run(args.model, 1, args.height, args.width, 1, 0, cores)
-    total = args.steps + args.warmup
-    sb = 1
-    for cand in (4, 2):
-        if probe * cand * total <= 150.0:
-            sb = cand
-            break
-    val, sec, thr = cpu_reference_run(args.model, sb, args.height, args.width, args.steps, args.warmup, cores)
-    sample = (f"{args.model} fwd+loss+bwd+AdamW fp32 on a {sb}x3x{args.height}x{args.width} sample of the "
-              f"{args.batch}x3x{args.height}x{args.width} batch per step")
+    # a fixed batch-2 sample of the workload's geometry per step; the number of timed steps is cut
+    # (never below 5) so that the whole run stays near 3 minutes
+    sb = args.cpu_sample_batch
+    _, probe, _, _ = cpu_reference_run(args.model, sb, args.height, args.width, 1, 0, cores)
+    steps = max(5, min(args.steps, int(150.0 / probe) - args.warmup))
+    warm = max(1, min(args.warmup, 3))
+    val, sec, thr, kind = cpu_reference_run(args.model, sb, args.height, args.width, steps, warm, cores)
+    sample = (f"{steps} timed steps (+{warm} warm-up) of {args.model} fwd+loss+bwd+AdamW fp32 on a {sb}x3x{args.height}x"
+              f"{args.width} sample of the {args.batch}x3x{args.height}x{args.width} per-GPU batch, {sec:.2f} s/step, "
+              + ("the reference's own modules (oracle/_ref)" if kind == "reference" else "oracle port (oracle/_ref absent)"))
+    cfg = dict(workload_config(args), sample=sample, reference_sample_batch=sb, optimizer="torch.optim.AdamW")
     out = {"impl": "reference", "metric": metric_name(args),
-           "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": workload_config(args),
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+           "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -294,34 +303,31 @@ def run_b200(args):
     last_loss = loss.item()
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- end to end: host inputs, H2D inside the timed region, loss read back every step.
-    # The loop is what a training script with a pinned-memory loader does: the next batch is copied on a side stream
-    # while the current step computes, and the loss of step i is read on the host after step i+1 has been enqueued (one
-    # device->host read per step, without draining the GPU queue).
-    copy_stream = torch.cuda.Stream(device=dev)
-    slots = [[torch.empty_like(dev_x[0]), torch.empty_like(dev_t[0]), torch.cuda.Event(), torch.cuda.Event()]
-             for _ in range(2)]
-    for sl in slots:
-        sl[3].record()
+    # ---- end to end: HOST inputs through the library's own input stage (camvid_b200.data.DevicePrefetcher): uint8 HWC
+    # images + uint8 masks in pageable memory, as cv2 / the dataset yield them -> pinned ring -> side-stream H2D ->
+    # ToTensor + Normalize on the device (cvb_input_stage_u8) -> fp32 NCHW images + uint8 masks for net / loss. The
+    # loss of step i is read on the host after step i+1 has been enqueued (one device->host read per step without
+    # draining the queue), like a training script that prints the previous iteration's loss.
+    from camvid_b200 import data
+    host_u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8) for _ in range(nbuf)]
+    host_m8 = [t.to(torch.uint8) for t in host_t]
 
-    def prefetch(i):
-        sx, st, ev, consumed = slots[i % 2]
-        copy_stream.wait_event(consumed)  # the step that last read this slot has finished (not the one running now)
-        with torch.cuda.stream(copy_stream):
-            sx.copy_(host_x[i % nbuf], non_blocking=True)
-            st.copy_(host_t[i % nbuf], non_blocking=True)
-            ev.record(copy_stream)
+    class Loader:
+        def __init__(self, k):
+            self.k = k
+
+        def __len__(self):
+            return self.k
+
+        def __iter__(self):
+            for i in range(self.k):
+                yield host_u8[i % nbuf], host_m8[i % nbuf]
 
     def e2e_loop(k):
-        prefetch(0)
+        pf = data.DevicePrefetcher(Loader(k), dev, mask_dtype=torch.uint8)
         pending = None
-        for i in range(k):
-            sx, st, ev, consumed = slots[i % 2]
-            torch.cuda.current_stream().wait_event(ev)
-            loss_i = step(sx, st)
-            consumed.record()
-            if i + 1 < k:
-                prefetch(i + 1)
+        for x, m in pf:
+            loss_i = step(x, m)
             host_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
             host_loss.copy_(loss_i.detach(), non_blocking=True)
             done = torch.cuda.Event()
@@ -331,25 +337,55 @@ def run_b200(args):
                 float(pending[0])
             pending = (host_loss, done)
         pending[1].synchronize()
-        return float(pending[0])
+        return float(pending[0]), pf.h2d_bytes
 
-    e2e_loop(2)
+    e2e_loop(3)
     barrier()
     e0.record()
     w0 = time.perf_counter()
-    e2e_loop(args.steps)
+    _, h2d = e2e_loop(args.steps)
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
     e2e = {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": world * (host_x[0].numel() * 4 + host_t[0].numel() * 8), "d2h_bytes_per_step": 4 * world,
+           "h2d_bytes_per_step": world * h2d // args.steps, "d2h_bytes_per_step": 4 * world,
            "ms_per_step": e2e_ms / args.steps,
-           "how": "pinned host batches copied on a side stream (double-buffered), loss read back with a one-step lag"}
+           "how": "camvid_b200.data.DevicePrefetcher: uint8 HWC images + uint8 masks from pageable host memory, pinned "
+                  "ring, side-stream copy, ToTensor + Normalize on the device; loss read back with a one-step lag"}
+
+    # ---- data-parallel sanity (N > 1): the bucketed NCCL reducer against a plain all-reduce of rank-local gradients
+    dp_check = None
+    if world > 1:
+        def flat_grads():
+            return torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        x0, t0 = dev_x[0], dev_t[0]
+        opt.zero_grad(set_to_none=True)
+        loss_fn(net(x0), t0).backward()
+        g_dp = flat_grads().clone()
+        reducer = net.__dict__.pop("_cvb_reducer")
+        opt.zero_grad(set_to_none=True)
+        loss_fn(net(x0), t0).backward()
+        g_ref = flat_grads().clone()
+        net.__dict__["_cvb_reducer"] = reducer
+        g_local_norm = g_ref.norm().item()
+        dist.all_reduce(g_ref, op=dist.ReduceOp.AVG)
+        pf_ = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        pmax, pmin = pf_.clone(), pf_.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        dp_check = {"grad_rel_err": ((g_dp - g_ref).norm() / g_ref.norm()).item(),
+                    "grad_max_abs_err": (g_dp - g_ref).abs().max().item(),
+                    "mean_grad_norm": g_ref.norm().item(), "rank0_local_grad_norm": g_local_norm,
+                    "param_spread_over_ranks_max_abs": (pmax - pmin).abs().max().item(),
+                    "buckets": reducer.buckets_launched,
+                    "what": "gradients of one batch per rank through the bucketed side-stream reducer vs all_reduce(AVG) of "
+                            "the rank-local gradients of the same batches; max |param(rank i) - param(rank j)| after all steps"}
+        opt.zero_grad(set_to_none=True)
 
     # ---- per-kernel CUDA-event timing (same workload, K further steps)
     pk = peaks()
-    roofline, kernels = None, {}
+    roofline, roofline_wgrad, kernels = None, None, {}
     if not args.no_kernel_timing:
         from camvid_b200 import engine
         engine.OVERLAP_WGRAD = False  # one stream: every event pair brackets exactly one kernel
@@ -381,7 +417,7 @@ def run_b200(args):
                              "avg_us": round(sec / n * 1e6, 2), "share_of_step": round(sec / ksteps / step_s, 4)}
         top = kernels.get("conv3x3_fprop")
         if top:
-            roofline = {"kernel": "conv3x3 forward + data-gradient family (conv_fprop_kernel<256>, conv_fprop_halo_kernel<128>, conv_fprop_tr64_kernel)", "bound": "tensor",
+            roofline = {"kernel": "conv3x3 forward + data-gradient family (conv_fprop_kernel<256>, conv_fprop_tr128_kernel, conv_fprop_tr64_kernel)", "bound": "tensor",
                         "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s", "frac": top["frac"],
                         "peak_source": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                         "frac_of_burst_peak": round(top["achieved"] / pk["tf_burst"], 4),
@@ -389,6 +425,14 @@ def run_b200(args):
                         "algorithmic_bytes_per_launch": round(algo_bytes.get("conv3x3_fprop", 0.0) / max(agg["conv3x3_fprop"][2], 1)),
                         "avg_launch_us": top["avg_us"], "launches_per_step": top["launches_per_step"],
                         "share_of_step": top["share_of_step"]}
+        wg = kernels.get("conv3x3_wgrad")
+        if wg:
+            roofline_wgrad = {"kernel": "conv3x3 weight-gradient family (conv_wgrad_kernel<BN>, conv_wgrad_rs64_kernel, + split-K "
+                                        "part-sum / OIHW transpose)", "bound": "tensor", "achieved": wg["achieved"],
+                              "peak": wg["peak"], "unit": "TFLOP/s", "frac": wg["frac"],
+                              "frac_of_burst_peak": round(wg["achieved"] / pk["tf_burst"], 4),
+                              "traffic": traffic_from_profiles("conv3x3_wgrad"), "avg_launch_us": wg["avg_us"],
+                              "launches_per_step": wg["launches_per_step"], "share_of_step": wg["share_of_step"]}
 
     if rank != 0:
         if world > 1:
@@ -404,13 +448,17 @@ def run_b200(args):
            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks,
            "loss": last_loss, "conv_gflop_per_image": round(flops_img / 1e9, 2),
            "conv_tensor_util_end_to_end": round(value / world * flops_img / 1e12 / pk["tf_sustained"], 4),
-           "roofline": roofline, "kernels": kernels}
+           "roofline": roofline, "roofline_wgrad": roofline_wgrad, "kernels": kernels}
+    if dp_check is not None:
+        out["dp_check"] = dp_check
     if world == 1 and not args.no_cpu_baseline:
         sb = args.cpu_sample_batch
-        v, sec, thr = cpu_reference_run(args.model, sb, H, W, 3, 1)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
-                               "sample": f"3 timed steps (+1 warm-up) of the fp32 oracle port on a {sb}x3x{H}x{W} "
-                                         f"batch, {sec:.2f} s/step"}
+        v, sec, thr, kind = cpu_reference_run(args.model, sb, H, W, 5, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": kind,
+                               "sample": f"5 timed steps (+1 warm-up) of the reference train step (fwd + loss + bwd + "
+                                         f"AdamW, fp32) on a {sb}x3x{H}x{W} batch, {sec:.2f} s/step, "
+                                         + ("the reference's own modules (oracle/_ref)" if kind == "reference"
+                                            else "oracle port (oracle/_ref absent)")}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
