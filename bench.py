@@ -439,7 +439,8 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    plan = next(iter(net.__dict__["_plans"].values()))
+    from camvid_b200 import engine as _engine
+    plan = _engine.plans_of(net)[0]
     flops_img = sum(b.flops * (3 if i > 0 else 2) for i, b in enumerate(plan.blocks)) / B
     out = {"metric": metric_name(args), "value": value,
            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

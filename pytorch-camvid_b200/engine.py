@@ -8,6 +8,7 @@ C ABI (ops.py). Nothing is allocated per step except the flat fp32 gradient buff
 Reference topology: models/unet.py:35-156 and models/segnet.py:19-119; one "block" is the reference's
 BasicConv2d / BasicConv (conv3x3 pad 1 + BatchNorm2d + ReLU, models/unet.py:5-17, models/segnet.py:5-17).
 """
+import collections
 import itertools
 import os
 import weakref
@@ -199,7 +200,10 @@ class Plan:
         self.parts = torch.empty(max(self.stat_rows, self.reduce_rows), 2, 1024, device=device)
         self.blocks = []  # in forward order
         self.workspace = None
-        self.generation = 0
+        self.generation = 0           # bumped by every forward: the plan's activation buffers are overwritten
+        self.busy_generation = None   # generation whose saved activations a pending backward still needs
+        self.done_generation = None   # generation whose backward has run (y buffers now hold dy: no second backward)
+        self.generation_time = 0      # when the plan was last handed to a forward (pool replacement order)
         self.reducer = None  # parallel.GradReducer of the module during a backward pass (data parallelism)
         self.wstream = None  # side stream of the weight-gradient kernels during a backward pass
         self._wstream = None
@@ -539,6 +543,58 @@ class SegNetPlan(Plan):
         return self._end_backward(flat)
 
 
+class BlockPlan(Plan):
+    """One reference layer on its own -- BasicConv2d (models/unet.py:5-17), BasicConv (models/segnet.py:5-17) or
+    UpSample2d (bilinear x2 + BasicConv2d, models/unet.py:19-32) -- for callers that use a submodule of the drop-in
+    network directly (`net.down1(x)`, feature extraction, a hand-written forward). fp32 NCHW in / out like the reference
+    layer, the same kernels as inside the whole-network plans, gradients w.r.t. the input and the four parameters."""
+
+    def __init__(self, layer, conv, bn, upsample, n, h, w, device):
+        super().__init__(layer, n, h, w, device)
+        self.class_num = conv.out_channels
+        self.upsample = upsample
+        cin = conv.in_channels
+        self.src = self.buf(h, w, pad64(cin))
+        self.dsrc = torch.empty_like(self.src)
+        if upsample:
+            self.up, self.dup = self.buf(2 * h, 2 * w, pad64(cin)), self.buf(2 * h, 2 * w, pad64(cin))
+            xin, self.dxin, (ho, wo) = self.up, self.dup, (2 * h, 2 * w)
+        else:
+            xin, self.dxin, (ho, wo) = self.src, self.dsrc, (h, w)
+        self.ho, self.wo = ho, wo
+        self.out_a = self.buf(ho, wo, pad64(conv.out_channels))
+        self.d_out_a = torch.empty_like(self.out_a)
+        self.block = self.add("block", (conv, bn), xin, self.out_a)
+        self.finish()
+
+    def forward(self, x, train):
+        self.pack_weights()
+        ops.nchw_to_nhwc(x, self.src)
+        if self.upsample:
+            ops.bilinear2x(self.src, self.up)
+        if train:
+            self.block.forward_train()
+            self._bump_batches_tracked()
+        else:
+            self.block.forward_eval()
+        out = torch.empty(self.n, self.class_num, self.ho, self.wo, device=self.device)
+        ops.nhwc_to_nchw(self.out_a, out)
+        return out
+
+    def backward(self, dout, need_dx=True):
+        flat = self._begin_backward()
+        ops.nchw_to_nhwc(dout, self.d_out_a)
+        self.block.backward(self.d_out_a, self.dxin if need_dx else None, flat)
+        self._done(self.block)
+        dx = None
+        if need_dx:
+            if self.upsample:
+                ops.bilinear2x_bwd(self.dup, self.dsrc)
+            dx = torch.empty(self.n, self.block.cin, self.h, self.w, device=self.device)
+            ops.nhwc_to_nchw(self.dsrc, dx)
+        return self._end_backward(flat), dx
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # torch custom-op layer. The whole network is ONE dispatcher op per direction (`camvid_b200::net_forward` /
 # `camvid_b200::net_backward`, registered through torch.library with a fake (shape-only) implementation and an autograd
@@ -572,17 +628,27 @@ def _net_forward_fake(x, params, plan_handle, train):
     return x.new_empty(x.shape[0], _plan_of(plan_handle).class_num, x.shape[2], x.shape[3])
 
 
+def _check_generation(plan, generation):
+    if generation != plan.generation:
+        raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
+                           "later forward of the same module and input shape (each shape keeps CVB_PLANS_PER_SHAPE = "
+                           f"{PLANS_PER_SHAPE} sets of activation buffers; raise it to keep more forwards alive)")
+    if plan.done_generation == generation:
+        raise RuntimeError("camvid_b200: second backward() through the same forward pass (retain_graph) is not "
+                           "supported: the first one reused the saved conv outputs for their gradients")
+
+
 @torch.library.custom_op("camvid_b200::net_backward", mutates_args=())
 def net_backward_op(dlogits: torch.Tensor, plan_handle: int, generation: int) -> torch.Tensor:
     """Gradients of the loss w.r.t. every entry of `params` of the matching net_forward call, as ONE flat fp32 buffer
     (laid out in backward completion order, the unit of the data-parallel all-reduce buckets); Plan.grads_for slices it
     into per-parameter views."""
     plan = _plan_of(plan_handle)
-    if generation != plan.generation:
-        raise RuntimeError("camvid_b200: backward() of a forward pass whose saved activations were overwritten by a "
-                           "later forward of the same module and input shape (plans own one set of buffers)")
+    _check_generation(plan, generation)
     with ops.on_device(dlogits):  # autograd's worker thread of this device, but do not rely on it
-        return plan.backward(dlogits.float().contiguous())
+        flat = plan.backward(dlogits.float().contiguous())
+    plan.done_generation, plan.busy_generation = generation, None
+    return flat
 
 
 @net_backward_op.register_fake
@@ -590,10 +656,27 @@ def _net_backward_fake(dlogits, plan_handle, generation):
     return dlogits.new_empty(_plan_of(plan_handle).flat_size)
 
 
+class _Pending:
+    """Lives in the autograd context of a recorded forward: while it is alive a backward may still come, so the plan's
+    activation buffers must not be handed to another forward (run_module picks or builds another plan instead). Freed
+    with the graph -- `del loss`, the end of the iteration -- it releases the plan."""
+
+    def __init__(self, plan, generation):
+        self.plan, self.generation = weakref.ref(plan), generation
+        plan.busy_generation = generation
+
+    def __del__(self):
+        plan = self.plan()
+        if plan is not None and plan.busy_generation == self.generation:
+            plan.busy_generation = None
+
+
 def _net_setup_context(ctx, inputs, output):
     _, _, handle, train = inputs
     ctx.handle, ctx.train = handle, train
-    ctx.generation = _plan_of(handle).generation
+    plan = _plan_of(handle)
+    ctx.generation = plan.generation
+    ctx.pending = _Pending(plan, plan.generation) if train else None
 
 
 def _net_backward(ctx, dlogits):
@@ -607,30 +690,147 @@ def _net_backward(ctx, dlogits):
 net_forward_op.register_autograd(_net_backward, setup_context=_net_setup_context)
 
 
-def run_module(module, plan_cls, x):
-    """Shared forward of the drop-in modules: x fp32 NCHW CUDA -> logits fp32 NCHW."""
+# ---- one reference layer (BasicConv2d / BasicConv / UpSample2d) as a dispatcher op pair: like the network ops, plus the
+# gradient w.r.t. the input
+@torch.library.custom_op("camvid_b200::block_forward", mutates_args=())
+def block_forward_op(x: torch.Tensor, params: List[torch.Tensor], plan_handle: int, train: bool) -> torch.Tensor:
+    plan = _plan_of(plan_handle)
+    plan.generation += 1
+    with ops.on_device(x):
+        return plan.forward(x, train)
+
+
+@block_forward_op.register_fake
+def _block_forward_fake(x, params, plan_handle, train):
+    p = _plan_of(plan_handle)
+    return x.new_empty(x.shape[0], p.class_num, p.ho, p.wo)
+
+
+@torch.library.custom_op("camvid_b200::block_backward", mutates_args=())
+def block_backward_op(dout: torch.Tensor, plan_handle: int, generation: int, need_dx: bool) -> List[torch.Tensor]:
+    plan = _plan_of(plan_handle)
+    _check_generation(plan, generation)
+    with ops.on_device(dout):
+        flat, dx = plan.backward(dout.float().contiguous(), need_dx)
+    plan.done_generation, plan.busy_generation = generation, None
+    return [flat] + ([dx] if need_dx else [])
+
+
+@block_backward_op.register_fake
+def _block_backward_fake(dout, plan_handle, generation, need_dx):
+    p = _plan_of(plan_handle)
+    out = [dout.new_empty(p.flat_size)]
+    if need_dx:
+        out.append(dout.new_empty(p.n, p.block.cin, p.h, p.w))
+    return out
+
+
+def _block_setup_context(ctx, inputs, output):
+    x, _, handle, train = inputs
+    ctx.handle, ctx.train, ctx.need_dx = handle, train, x.requires_grad
+    plan = _plan_of(handle)
+    ctx.generation = plan.generation
+    ctx.pending = _Pending(plan, plan.generation) if train else None
+
+
+def _block_backward(ctx, dout):
+    if not ctx.train:
+        raise RuntimeError("camvid_b200: backward() through an eval-mode forward is not supported; call .train() first")
+    res = block_backward_op(dout, ctx.handle, ctx.generation, ctx.need_dx)
+    return (res[1] if ctx.need_dx else None), _plan_of(ctx.handle).grads_for(res[0]), None, None
+
+
+block_forward_op.register_autograd(_block_backward, setup_context=_block_setup_context)
+
+
+# ---- plan cache of a module: per input geometry a small pool of plans (= sets of activation buffers), least recently
+# used geometries evicted
+PLANS_PER_SHAPE = int(os.environ.get("CVB_PLANS_PER_SHAPE", "2"))  # forwards of one shape that may await their backward
+MAX_SHAPES = int(os.environ.get("CVB_MAX_SHAPES", "4"))            # input geometries kept per module
+
+
+def plans_of(module):
+    """Every live plan of a drop-in module, most recently used geometry last (introspection: tests, bench.py)."""
+    return [p for pool in module.__dict__.get("_plans", {}).values() for p in pool]
+
+
+def _acquire_plan(module, key, build):
+    """The plan a forward of geometry `key` runs on. A plan whose last recorded forward still awaits its backward is
+    skipped when another one is free or may be built (up to PLANS_PER_SHAPE per geometry), so two forwards before a
+    backward -- a validation pass inside the training step, gradient accumulation over differently shaped inputs, a
+    GAN-style double forward -- work; beyond that the oldest pending forward is overwritten and ITS backward raises.
+    Geometries not used recently are dropped (MAX_SHAPES; a ragged last batch no longer pins a second 14 GB plan set
+    forever) unless a backward is still pending on them."""
+    cache = module.__dict__.setdefault("_plans", collections.OrderedDict())
+    pool = cache.get(key)
+    if pool is not None and any(b.conv.weight.device.index != key[-1] for p in pool for b in p.blocks[:1]):
+        pool = None  # the module moved to another device
+    if pool is None:
+        pool = cache[key] = []
+    cache.move_to_end(key)
+    plan = next((p for p in pool if p.busy_generation is None), None)
+    if plan is None:
+        if len(pool) < PLANS_PER_SHAPE:
+            # buffer allocation is not part of the traced computation (writer.add_graph traces the first forward)
+            tracing = torch._C._get_tracing_state()
+            torch._C._set_tracing_state(None)
+            try:
+                plan = build()
+            finally:
+                torch._C._set_tracing_state(tracing)
+            pool.append(plan)
+        else:
+            plan = min(pool, key=lambda p: p.generation_time)
+    plan.generation_time = next(_CLOCK)
+    while len(cache) > MAX_SHAPES:
+        victim = next((k for k, v in cache.items() if k != key and all(p.busy_generation is None for p in v)), None)
+        if victim is None:
+            break
+        del cache[victim]
+    return plan
+
+
+_CLOCK = itertools.count(1)
+
+
+def _check_input(x, channels, what):
     if not x.is_cuda:
         raise RuntimeError("camvid_b200 runs on CUDA (sm_100a) only: move the module and its input to the GPU; "
                            "there is no CPU path")
-    if x.dim() != 4 or x.shape[1] != module.input_channels:
-        raise RuntimeError(f"expected input [N,{module.input_channels},H,W], got {tuple(x.shape)}")
+    if x.dim() != 4 or x.shape[1] != channels:
+        raise RuntimeError(f"{what}: expected input [N,{channels},H,W], got {tuple(x.shape)}")
+
+
+def run_module(module, plan_cls, x):
+    """Shared forward of the drop-in modules: x fp32 NCHW CUDA -> logits fp32 NCHW."""
+    _check_input(x, module.input_channels, type(module).__name__)
     if x.shape[1] * 9 > 64:
         raise RuntimeError("input_channels > 7 is not supported by the first-layer im2col kernel")
     if x.shape[2] < 32 or x.shape[3] < 32:
         raise RuntimeError("input must be at least 32x32 (five 2x2 poolings)")
     x = x.detach().float().contiguous()
     n, h, w = int(x.shape[0]), int(x.shape[2]), int(x.shape[3])  # concrete even under torch.jit.trace
-    key = (n, h, w, x.device.index)
-    plans = module.__dict__.setdefault("_plans", {})
-    plan = plans.get(key)
-    if plan is None or any(b.conv.weight.device != x.device for b in plan.blocks[:1]):
-        # buffer allocation is not part of the traced computation (writer.add_graph traces the first forward)
-        tracing = torch._C._get_tracing_state()
-        torch._C._set_tracing_state(None)
-        try:
-            with ops.on_device(x):
-                plan = plan_cls(module, n, h, w, x.device)
-        finally:
-            torch._C._set_tracing_state(tracing)
-        plans[key] = plan
+
+    def build():
+        with ops.on_device(x):
+            return plan_cls(module, n, h, w, x.device)
+
+    plan = _acquire_plan(module, (n, h, w, x.device.index), build)
     return net_forward_op(x, plan.param_list(), plan.handle, bool(module.training))
+
+
+def run_block(layer, conv, bn, x, upsample=False):
+    """Forward of ONE reference layer used on its own (BasicConv2d / BasicConv / UpSample2d .forward): fp32 NCHW in,
+    fp32 NCHW out, differentiable w.r.t. the input and the layer's parameters."""
+    _check_input(x, conv.in_channels, type(layer).__name__)
+    if x.shape[2] < 2 or x.shape[3] < 2:
+        raise RuntimeError("input must be at least 2x2")
+    xin = x.float().contiguous()
+    n, h, w = int(x.shape[0]), int(x.shape[2]), int(x.shape[3])
+
+    def build():
+        with ops.on_device(x):
+            return BlockPlan(layer, conv, bn, upsample, n, h, w, x.device)
+
+    plan = _acquire_plan(layer, (n, h, w, x.device.index), build)
+    return block_forward_op(xin, plan.param_list(), plan.handle, bool(layer.training))

@@ -15,6 +15,9 @@ class BasicConv(nn.Module):
         self.bn = nn.BatchNorm2d(out_channels)
         self.relu = nn.ReLU()
 
+    def forward(self, x):  # models/segnet.py:14-17, through engine.run_block (the whole network runs one plan instead)
+        return engine.run_block(self, self.conv, self.bn, x)
+
 
 class SegNet(nn.Module):
     # (stage name, channel chain) in construction order, models/segnet.py:23-77

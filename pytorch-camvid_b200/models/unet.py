@@ -2,7 +2,9 @@
 and default initialisation order -- but forward() runs the B200 kernel plan (engine.UNetPlan) instead of ATen ops.
 
 Reference: models/unet.py:5-17 (BasicConv2d), :19-32 (UpSample2d), :35-92 (UNet.__init__), :94-156 (forward).
-The torch submodules below are parameter containers only; their own forward() is never on the hot path.
+UNet.forward runs one plan for the whole network; BasicConv2d / UpSample2d also have a forward of their own (the same
+kernels through engine.run_block) so that code using a sub-layer directly -- `net.down1(x)`, feature extraction, a
+custom forward -- keeps working like with the reference modules.
 """
 import torch.nn as nn
 
@@ -17,6 +19,9 @@ class BasicConv2d(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_channels, out_channels, 3, padding=1), nn.BatchNorm2d(out_channels),
                                   nn.ReLU(inplace=True))
 
+    def forward(self, x):  # models/unet.py:16-17
+        return engine.run_block(self, self.conv[0], self.conv[1], x)
+
 
 class UpSample2d(nn.Module):
     """bilinear x2 (align_corners=True) followed by a BasicConv2d, models/unet.py:19-32."""
@@ -25,6 +30,9 @@ class UpSample2d(nn.Module):
         super().__init__()
         self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
         self.conv = BasicConv2d(in_channels, out_channels)
+
+    def forward(self, x):  # models/unet.py:28-32: upsample and conv block in one plan
+        return engine.run_block(self, self.conv.conv[0], self.conv.conv[1], x, upsample=True)
 
 
 class UNet(nn.Module):

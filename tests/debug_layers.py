@@ -28,7 +28,8 @@ rec = O.RECORD
 O.RECORD = None
 logits = net(x.cuda())
 loss = CrossEntropyLoss()(logits, t.cuda())
-plan = next(iter(net.__dict__["_plans"].values()))
+from camvid_b200 import engine
+plan = engine.plans_of(net)[0]
 torch.cuda.synchronize()
 print("loss", loss.item(), o_loss.item(), "logits rel", rel_err(logits.cpu(), o_logits))
 for b in plan.blocks:

@@ -88,7 +88,8 @@ def test_blocks_at_baseline_geometry(cutils, cuda, name, n, h, w):
     net = cutils.get_model(name, 3, 12).to(cuda).train()
     with torch.no_grad():
         net(torch.zeros(n, 3, h, w, device=cuda))  # builds the plan (and its buffers) for this geometry
-    plan = next(iter(net.__dict__["_plans"].values()))
+    from camvid_b200 import engine
+    plan = engine.plans_of(net)[0]
     flat = torch.zeros(plan.flat_size, device=cuda)
     seen, worst = set(), {}
 
