@@ -53,6 +53,17 @@ inline int check_view(const cvb_view& v, const char* name) {
   return CVB_OK;
 }
 
+// development knob shared by the strip-marching kernels: rows of L2 prefetch distance (CVB_PREFETCH_ROWS, default 4)
+inline int prefetch_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVB_PREFETCH_ROWS");
+    v = e ? atoi(e) : 4;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
 inline bool same_shape(const cvb_view& a, const cvb_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -137,6 +148,9 @@ __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(re
 __device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 // streaming variants for single-use data (evict-first: keep L2 for the tensors the next kernel re-reads)
 __device__ __forceinline__ uint4 ldg16_cs(const __nv_bfloat16* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+// L2 prefetch of the 128-byte line holding p: costs no register and no scoreboard entry, so a thread that walks a strip
+// row by row (dependent iterations, few loads in flight) can keep several ROWS of DRAM requests outstanding
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
   float4 a = __ldg(reinterpret_cast<const float4*>(p));
   float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);

@@ -33,7 +33,7 @@ __device__ __forceinline__ void lerp_row(const __nv_bfloat16* p0, const __nv_bfl
 // Consecutive threads = consecutive channel vectors, then consecutive columns: every access of a warp is one
 // contiguous run.
 __global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View out, float sy, float sx, int rows,
-                                                                   int strips) {
+                                                                   int strips, int pf) {
   const unsigned CV = static_cast<unsigned>(x.c) >> 3;
   const unsigned total = 1u * out.n * strips * out.w * CV;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View o
       float ly0, ly1;
       src_index(sy, oy, x.h, y0, y1, ly0, ly1);
       if (y0 != r) {
+        if (pf > 0 && y1 + pf < x.h) {  // the source row needed `pf` source rows from now: start its DRAM fetch
+          prefetch_l2(c0 + (y1 + pf) * x.sh);
+          prefetch_l2(c1 + (y1 + pf) * x.sh);
+        }
         if (y0 == r + 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) ra[j] = rb[j];
@@ -111,7 +115,7 @@ __device__ __forceinline__ int gather_taps(float scale, float inv, int in, int o
 // its input column, found once per thread) and adds the result into two rolling row accumulators (source rows y0 and
 // y0 + 1 of that output row). 4-5 loads per output row instead of 16-25 per input pixel.
 __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, View dx, float sy, float sx, float isy,
-                                                                   float isx, int rows, int strips) {
+                                                                   float isx, int rows, int strips, int pf) {
   const unsigned CV = static_cast<unsigned>(dx.c) >> 3;
   const unsigned total = 1u * dx.n * strips * dx.w * CV;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
@@ -149,6 +153,12 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, Vie
         ++r;
       }
       const __nv_bfloat16* rowp = src + oy * dout.sh;
+      if (pf > 0 && oy + pf <= hi) {  // the iterations are dependent (one row of taps in flight per thread): keep `pf`
+        const __nv_bfloat16* ahead = rowp + pf * dout.sh;  // further rows of DRAM requests outstanding through L2
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+          if (b < nx) prefetch_l2(ahead + ox[b] * dout.sw);
+      }
       uint4 u[6];
 #pragma unroll
       for (int b = 0; b < 6; ++b) u[b] = b < nx ? ldg16(rowp + ox[b] * dout.sw) : make_uint4(0u, 0u, 0u, 0u);
@@ -210,7 +220,7 @@ extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float fsy = ac_scale(x.h, out.h), fsx = ac_scale(x.w, out.w);
-  bilinear2x_fwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips);
+  bilinear2x_fwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips, prefetch_rows());
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -231,7 +241,8 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   long long total = 1LL * dx.n * strips * dx.w * cv;
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bilinear2x_bwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips);
+  bilinear2x_bwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
+                                                   prefetch_rows());
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -32,7 +32,10 @@ class _CEFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dl = ctx.dl
-        ctx.dl = None
+        ctx.dl = None  # the gradient was computed with the loss; it is handed over (scaled in place), not kept
+        if dl is None:
+            raise RuntimeError("camvid_b200.nn.CrossEntropyLoss: second backward() through the same loss value is not "
+                               "supported (its gradient buffer was released by the first)")
         return dl.mul_(g), None, None, None
 
 

@@ -496,8 +496,12 @@ def test_several_forwards_before_a_backward(cvb, cuda):
         l1.backward()
     l2.backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="second backward"):
-        l2.backward()
+        l2.backward()  # (the fused loss says so first; below, the plan itself through a plain torch reduction)
     l3.backward()
+    s = net(xa.to(cuda)).sum()
+    s.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        s.backward()
 
 
 def test_plan_cache_evicts_old_geometries(cvb, cuda):
