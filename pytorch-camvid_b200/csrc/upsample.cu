@@ -241,7 +241,12 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   long long total = 1LL * dx.n * strips * dx.w * cv;
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bilinear2x_bwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
+  static int dbg_smem = -1;  // experiment (CVB_BILINEAR_SMEM bytes): would a shared-memory kernel still co-run with the wgrad CTAs?
+  if (dbg_smem < 0) {
+    const char* e = getenv("CVB_BILINEAR_SMEM");
+    dbg_smem = e ? atoi(e) : 0;
+  }
+  bilinear2x_bwd_kernel<<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
                                                    prefetch_rows());
   CVB_LAUNCH_CHECK();
   return CVB_OK;
