@@ -385,12 +385,23 @@ def run_b200(args):
 
     # ---- per-kernel CUDA-event timing (same workload, K further steps)
     pk = peaks()
-    roofline, roofline_wgrad, kernels = None, None, {}
+    roofline, roofline_wgrad, kernels, diagnostics = None, None, {}, None
     if not args.no_kernel_timing:
         from camvid_b200 import engine
         engine.OVERLAP_WGRAD = False  # one stream: every event pair brackets exactly one kernel
-        rec = ops.profile(True)
         ksteps = min(args.steps, 10)
+        # diagnostic: the same steps on ONE stream without the event pairs -- minus the sum of the kernel times below, this
+        # is what the gaps between dependent launches cost
+        for i in range(2):
+            step(dev_x[i % nbuf], dev_t[i % nbuf])
+        barrier()
+        e0.record()
+        for i in range(ksteps):
+            step(dev_x[i % nbuf], dev_t[i % nbuf])
+        e1.record()
+        barrier()
+        serial_ms = e0.elapsed_time(e1) / ksteps
+        rec = ops.profile(True)
         barrier()
         for i in range(ksteps):
             step(dev_x[i % nbuf], dev_t[i % nbuf])
@@ -407,6 +418,9 @@ def run_b200(args):
             if len(work) > 3:
                 algo_bytes[what] = algo_bytes.get(what, 0.0) + work[3]
         step_s = sum(d[0] for d in agg.values()) / ksteps
+        diagnostics = {"single_stream_ms_per_step": round(serial_ms, 3), "kernel_time_sum_ms_per_step": round(step_s * 1e3, 3),
+                       "launch_gap_ms_per_step": round(serial_ms - step_s * 1e3, 3),
+                       "what": "one stream, weight gradients not overlapped: step time vs the sum of its kernels' durations"}
         for what, (sec, amount, n, kind) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             if kind == "flops":
                 ach, peak, unit, bound = amount / sec / 1e12, pk["tf_sustained"], "TFLOP/s", "tensor"
@@ -449,7 +463,7 @@ def run_b200(args):
            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks,
            "loss": last_loss, "conv_gflop_per_image": round(flops_img / 1e9, 2),
            "conv_tensor_util_end_to_end": round(value / world * flops_img / 1e12 / pk["tf_sustained"], 4),
-           "roofline": roofline, "roofline_wgrad": roofline_wgrad, "kernels": kernels}
+           "roofline": roofline, "roofline_wgrad": roofline_wgrad, "kernels": kernels, "diagnostics": diagnostics}
     if dp_check is not None:
         out["dp_check"] = dp_check
     if world == 1 and not args.no_cpu_baseline:

@@ -59,6 +59,7 @@ SIGNATURES = {
     "cvb_maxpool2x2_fwd": (_I, [View, View, _P, _P]),
     "cvb_bn_relu_maxpool2x2_fwd": (_I, [View, _P, _P, View, View, _P, _P]),
     "cvb_maxpool2x2_bwd": (_I, [View, _P, View, View, _I, _P]),
+    "cvb_maxpool2x2_bwd_bn_reduce": (_I, [View, _P, View, _P, _P, View, _I, _P, _I, _P]),
     "cvb_maxunpool2x2_fwd": (_I, [View, _P, View, _P]),
     "cvb_maxunpool2x2_bwd": (_I, [View, _P, View, _P]),
     "cvb_pool_code_to_index": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),

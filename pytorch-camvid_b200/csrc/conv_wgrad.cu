@@ -473,38 +473,26 @@ conv_wgrad_rs64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   }
 }
 
-// Part reduction, phase 1: slot 0 += slots 1 .. parts-1 of the item an element belongs to (16-byte accesses; the item and
-// its part count follow from the element's position with the same integer arithmetic the main kernel uses).
-__global__ void __launch_bounds__(256) wgrad_partsum_kernel(float* __restrict__ ws, WgradParams p, int BN) {
-  const long long n4 = 1LL * p.taps * p.cin_pad * p.cout_pad / 4;
-  float4* base = reinterpret_cast<float4*>(ws);
-  const int co4 = p.cout_pad / 4;
-  for (long long i = 1LL * blockIdx.x * 256 + threadIdx.x; i < n4; i += 1LL * gridDim.x * 256) {
-    const int co = static_cast<int>(i % co4) * 4;
-    const long long t = i / co4;
-    const int ci = static_cast<int>(t % p.cin_pad);
-    const int tap = static_cast<int>(t / p.cin_pad);
-    const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co / BN;
-    int w = 0;
-    while (w + 1 < p.n_waves && item >= p.wave_item0[w + 1]) ++w;
-    const long long wu = 1LL * p.wave_items[w] * p.total_tiles, u0 = 1LL * (item - p.wave_item0[w]) * p.total_tiles;
-    const int parts = sk_owner(wu, p.wave_grid[w], u0 + p.total_tiles - 1) - sk_owner(wu, p.wave_grid[w], u0) + 1;
-    float4 acc = base[i];
-    for (int s = 1; s < parts; ++s) {
-      const float4 v = __ldcs(base + s * n4 + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    base[i] = acc;
-  }
+// Number of workspace parts (= CTAs whose unit range touched it) of a work item: the same integer arithmetic the main
+// kernel uses for its ranges.
+__device__ __forceinline__ int item_parts(const WgradParams& p, int item) {
+  int w = 0;
+  while (w + 1 < p.n_waves && item >= p.wave_item0[w + 1]) ++w;
+  const long long wu = 1LL * p.wave_items[w] * p.total_tiles, u0 = 1LL * (item - p.wave_item0[w]) * p.total_tiles;
+  return sk_owner(wu, p.wave_grid[w], u0 + p.total_tiles - 1) - sk_owner(wu, p.wave_grid[w], u0) + 1;
 }
 
-// out[co][ci][tap] = sum_s ws[s][tap][ci][co].  A block owns a brick of 32 co x BCI ci x all taps: it sums the splits with
-// coalesced 128-byte reads (co fastest), transposes the brick through shared memory and writes runs of BCI*taps
-// contiguous floats per co row of the OIHW tensor. BCI shrinks for small layers so that the grid still fills the GPU.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps,
-                                                           int cin_pad, int cout_pad, int cout, int cin_eff, int bci,
+// out[co][ci][tap] = sum over the parts s of the item that owns the element of ws[s][tap][ci][co].  ONE kernel for the
+// split-K reduction and the transposition to nn.Conv2d.weight.grad's OIHW layout (round 1 ran two, 46 launches per UNet
+// step). A block owns a brick of 32 co x BCI ci x all taps: it sums the parts with coalesced 128-byte reads (co fastest;
+// the part count is a property of the (tap, ci) row: a 32-wide co run never straddles a co tile), transposes the brick
+// through shared memory and writes runs of BCI*taps contiguous floats per co row. BCI shrinks for small layers so that
+// the grid still fills the GPU. Deterministic: fixed summation order, no atomics.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, const WgradParams p, int BN,
+                                                           int cout, int cin_eff, int x_c, int bci,
                                                            float* __restrict__ out) {
   extern __shared__ float tile[];  // [taps][bci][33]
+  const int taps = p.taps, cin_pad = p.cin_pad, cout_pad = p.cout_pad;
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * bci;
   const int tx = threadIdx.x & 31;
   const long long split_stride = 1LL * taps * cin_pad * cout_pad;
@@ -513,16 +501,18 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const int tap = e / bci, i = e - tap * bci;
     const int ci = ci0 + i, co = co0 + tx;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (ci < cin_pad && co < cout_pad) {
+    if (ci < cin_pad && ci < x_c && co < cout_pad) {
+      const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co0 / BN;
+      const int parts = item_parts(p, item);
       const float* src = ws + (1LL * tap * cin_pad + ci) * cout_pad + co;
       int s = 0;
-      for (; s + 3 < splits; s += 4) {  // four independent loads in flight
-        a0 += src[s * split_stride];
-        a1 += src[(s + 1) * split_stride];
-        a2 += src[(s + 2) * split_stride];
-        a3 += src[(s + 3) * split_stride];
+      for (; s + 3 < parts; s += 4) {  // four independent loads in flight
+        a0 += __ldcs(src + s * split_stride);
+        a1 += __ldcs(src + (s + 1) * split_stride);
+        a2 += __ldcs(src + (s + 2) * split_stride);
+        a3 += __ldcs(src + (s + 3) * split_stride);
       }
-      for (; s < splits; ++s) a0 += src[s * split_stride];
+      for (; s < parts; ++s) a0 += __ldcs(src + s * split_stride);
     }
     tile[(tap * bci + i) * 33 + tx] = (a0 + a1) + (a2 + a3);
   }
@@ -758,14 +748,9 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   const int cin_pad = plan.p.cin_pad, cout_pad = plan.p.cout_pad;
   int bci = 32;
   while (bci > 2 && 1LL * ((cout_pad + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
-  if (plan.p.slots > 1) {
-    const long long n4 = 1LL * taps * cin_pad * cout_pad / 4;
-    wgrad_partsum_kernel<<<ew_grid(n4, 256, 16), 256, 0, st>>>(plan.p.ws, plan.p, plan.BN);
-    CVB_LAUNCH_CHECK();
-  }
   dim3 rgrid((cout_pad + 31) / 32, (x.c + bci - 1) / bci);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, 1, taps, cin_pad, cout_pad, cout, cin_eff,
-                                                                          bci, dw);
+  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, plan.p, plan.BN, cout, cin_eff, x.c, bci,
+                                                                          dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -29,6 +29,9 @@ OVERLAP_WGRAD = True
 # Off by default: measured 1 % slower end to end -- the reduce pass it removes was already hidden under the side-stream
 # weight gradient, while the heavier epilogue lengthens the data gradient on the critical path (CVB_FUSE_BWD=1 enables).
 FUSE_BWD_STATS = os.environ.get("CVB_FUSE_BWD", "0") != "0"
+# MaxPool backward emits the BatchNorm+ReLU backward reduction of the block it feeds (cvb_maxpool2x2_bwd_bn_reduce): the
+# reduce pass over the largest activations of the encoder disappears (4 of 23 passes in UNet, 5 of 26 in SegNet).
+FUSE_POOL_BWD_REDUCE = os.environ.get("CVB_FUSE_POOL_BWD", "1") != "0"
 SERIALIZE_TENSOR_KERNELS = os.environ.get("CVB_SERIALIZE_TENSOR", "0") != "0"  # measured: see DESIGN.md knobs
 
 
@@ -144,8 +147,10 @@ class Block:
         ops.WORK_SCALE = self.c_ratio
         if self.ce != da.shape[3]:
             da = da[..., :self.ce]
-        rows = p.stat_rows
-        if not stats_ready:
+        # stats_ready: False = reduce here; True = the data-gradient conv that produced da emitted the partial sums
+        # (stat_rows of them); an int = another producer did (that many rows)
+        rows = p.stat_rows if stats_ready is True else stats_ready
+        if stats_ready is False:
             ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows)
             rows = p.reduce_rows
         dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
@@ -431,8 +436,14 @@ class UNetPlan(Plan):
                 ch = self.cat[l].shape[3] // 2
                 da = self.dcat[l][..., ch:]
                 # encoder activation feeds both the skip (already in dcat) and the pool: add the pool path
-                ops.maxpool2x2_bwd(self.dpooled[l], da, x=b1.a, accumulate=True)
-            ready = b1.backward(da, self.d_enc_mid[l], flat, consumer=b0)
+                if FUSE_POOL_BWD_REDUCE and b1.ce == da.shape[3]:
+                    ops.maxpool2x2_bwd_bn_reduce(self.dpooled[l], da, b1.y_e, b1.vec[2], b1.vec[3],
+                                                 self.parts_view(b1.ce), self.reduce_rows, accumulate=True)
+                    pooled_ready = self.reduce_rows
+                else:
+                    ops.maxpool2x2_bwd(self.dpooled[l], da, x=b1.a, accumulate=True)
+                    pooled_ready = False
+            ready = b1.backward(da, self.d_enc_mid[l], flat, consumer=b0, stats_ready=pooled_ready if l < 4 else False)
             self._done(b1)
             b0.backward(self.d_enc_mid[l], self.dpooled[l - 1] if l > 0 else None, flat, stats_ready=ready)
             self._done(b0)
@@ -530,8 +541,13 @@ class SegNetPlan(Plan):
         for s in range(4, -1, -1):
             st = self.stages[s]
             bl = st["blocks"]
-            ops.maxpool2x2_bwd(st["dpooled"], st["dacts"][-1], code=st["code"])
-            ready = False
+            if FUSE_POOL_BWD_REDUCE and bl[-1].ce == st["dacts"][-1].shape[3]:
+                ops.maxpool2x2_bwd_bn_reduce(st["dpooled"], st["dacts"][-1], bl[-1].y_e, bl[-1].vec[2], bl[-1].vec[3],
+                                             self.parts_view(bl[-1].ce), self.reduce_rows, code=st["code"])
+                ready = self.reduce_rows
+            else:
+                ops.maxpool2x2_bwd(st["dpooled"], st["dacts"][-1], code=st["code"])
+                ready = False
             for j in range(len(bl) - 1, -1, -1):
                 if j > 0:
                     dx = st["dacts"][j - 1]

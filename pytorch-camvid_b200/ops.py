@@ -241,7 +241,7 @@ def conv3x3_wgrad(x, dy, dw, taps=9, workspace=None, algo_flops=None):
         workspace = torch.empty(conv3x3_wgrad_workspace_bytes(x, dy, taps), dtype=torch.uint8, device=x.device)
     if algo_flops is None:
         algo_flops = 2.0 * taps * x.shape[3] * dy.shape[3] * dy.shape[0] * dy.shape[1] * dy.shape[2]
-    _call("conv3x3_wgrad", 3, ("flops", algo_flops, f"{tuple(x.shape)}->{dy.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
+    _call("conv3x3_wgrad", 2, ("flops", algo_flops, f"{tuple(x.shape)}->{dy.shape[3]} taps{taps}"), _lib.load().cvb_conv3x3_wgrad, view(x), view(dy), taps, _ptr(dw),
           cout, cin, _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     return dw
 
@@ -299,6 +299,14 @@ def maxpool2x2_bwd(dout, dx, code=None, x=None, accumulate=False):
     _call("maxpool2x2_bwd", 1, _nbytes(dout, dx, code, x, dx if accumulate else None),
           _lib.load().cvb_maxpool2x2_bwd, view(dout), _ptr(code), view(x), view(dx), 1 if accumulate else 0,
           _stream())
+    return dx
+
+
+def maxpool2x2_bwd_bn_reduce(dout, dx, y, scale, shift, partials, rows, code=None, accumulate=False):
+    """maxpool2x2_bwd + bn_relu_bwd_reduce of the pooled block in one pass over dx (see the header)."""
+    _call("maxpool2x2_bwd_bn_reduce", 1, _nbytes(dout, dx, code, y, dx if accumulate else None),
+          _lib.load().cvb_maxpool2x2_bwd_bn_reduce, view(dout), _ptr(code), view(y), _ptr(scale), _ptr(shift), view(dx),
+          1 if accumulate else 0, _ptr(partials), rows, _stream())
     return dx
 
 

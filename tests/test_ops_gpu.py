@@ -365,6 +365,39 @@ def test_bilinear2x(ops, cuda, n, h, w, c):
     assert rel_err(to_nchw_f32(dx), dx_ref) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 24, 64), (1, 45, 61, 128), (3, 11, 15, 1024), (2, 9, 8, 16)])
+@pytest.mark.parametrize("mode", ["unet", "segnet"])
+def test_maxpool_bwd_fused_with_bn_reduce_is_bit_identical(ops, cuda, n, h, w, c, mode):
+    """cvb_maxpool2x2_bwd_bn_reduce (cross-layer fusion, producer side) against the two kernels it replaces on the same
+    buffers: dx bit-identical, reduction partials summing to the same (sum g, sum g*y) up to fp32 summation order.
+    unet: accumulate into the skip gradient, argmax recomputed from relu(bn(y)); segnet: scatter by the stored codes."""
+    torch.manual_seed(33)
+    y = _rand((n, h, w, c), cuda, 70).to(torch.bfloat16)
+    scale = (torch.rand(c, device=cuda) + 0.5) * torch.where(torch.rand(c, device=cuda) < 0.2, -1.0, 1.0)  # some gamma < 0
+    shift = torch.randn(c, device=cuda) * 0.3
+    a = torch.empty_like(y)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=cuda)
+    code = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=cuda)
+    ops.bn_relu_maxpool2x2(y, scale, shift, a, pooled, code)  # the forward that produced the activation and the codes
+    dout = _rand((n, h // 2, w // 2, c), cuda, 71).to(torch.bfloat16)
+    skip = _rand((n, h, w, c), cuda, 72).to(torch.bfloat16)
+    rows = 3 * 37
+    acc = mode == "unet"
+    # reference: the unfused pair
+    dx_ref = skip.clone() if acc else torch.full_like(skip, 7.0)
+    ops.maxpool2x2_bwd(dout, dx_ref, code=None if acc else code, x=a if acc else None, accumulate=acc)
+    parts_ref = torch.zeros(rows, 2, c, device=cuda)
+    ops.bn_relu_bwd_reduce(dx_ref, y, scale, shift, parts_ref, rows)
+    # fused
+    dx = skip.clone() if acc else torch.full_like(skip, 7.0)
+    parts = torch.full((rows, 2, c), float("nan"), device=cuda)
+    ops.maxpool2x2_bwd_bn_reduce(dout, dx, y, scale, shift, parts, rows, code=None if acc else code, accumulate=acc)
+    assert torch.equal(dx, dx_ref)
+    s, s_ref = parts.double().sum(0), parts_ref.double().sum(0)
+    assert torch.isfinite(s).all()
+    torch.testing.assert_close(s, s_ref, rtol=1e-5, atol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------- loss / metric
 @pytest.mark.parametrize("hw", [(17, 23), (16, 24)])  # generic kernel / four-pixel vectorised 12-class kernel
 @pytest.mark.parametrize("ignore", [-100, 11])

@@ -50,6 +50,11 @@ timeit("bn_relu_bwd_reduce", lambda: ops.bn_relu_bwd_reduce(da, y, scale, shift,
 timeit("bn_relu_bwd_apply", lambda: ops.bn_relu_bwd_apply(da, y, scale, shift, coef, dy), 6 * E)
 timeit("bn_relu_maxpool", lambda: ops.bn_relu_maxpool2x2(y, scale, shift, a, pooled), 4 * E + E // 2)
 timeit("maxpool_bwd(recompute)", lambda: ops.maxpool2x2_bwd(pooled, dy, x=a, accumulate=True), 6 * E + E // 2)
+da2 = da.clone()
+timeit("pool_bwd+reduce (2 kernels)", lambda: (ops.maxpool2x2_bwd(pooled, da2, x=a, accumulate=True),
+                                              ops.bn_relu_bwd_reduce(da2, y, scale, shift, parts, rows)), 10 * E + E // 2)
+timeit("pool_bwd_bn_reduce fused", lambda: ops.maxpool2x2_bwd_bn_reduce(pooled, da2, y, scale, shift, parts, rows, accumulate=True),
+       6 * E + E // 2)
 if up is not None:
     timeit("bilinear2x_fwd", lambda: ops.bilinear2x(y, up), 2 * E + 8 * E)
     timeit("bilinear2x_bwd", lambda: ops.bilinear2x_bwd(up, dy), 2 * E + 8 * E)
