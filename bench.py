@@ -56,6 +56,8 @@ def parse():
                     help="eval: BASELINE config 5 (forward with running statistics + argmax + confusion matrix / mIoU)")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"],
                     help="b200 = camvid_b200.optim.AdamW (fused drop-in, parity-tested against torch); torch = torch.optim.AdamW")
+    ap.add_argument("--graph", action="store_true",
+                    help="also time the step as ONE CUDA graph replay (camvid_b200.graph.GraphedTrainStep; single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
@@ -293,8 +295,10 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(dev_x[i % nbuf], dev_t[i % nbuf])
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # host time to ENQUEUE a step (the GPU runs behind)
     e1.record()
     barrier()
     clocks = sampler.result()
@@ -302,6 +306,30 @@ def run_b200(args):
     launches = (ops.LAUNCHES - l0) // args.steps
     last_loss = loss.item()
     value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- the same step as one CUDA graph replay (optional)
+    graph_info = None
+    if args.graph and world == 1 and args.optimizer == "b200":
+        from camvid_b200.graph import GraphedTrainStep
+        gopt = AdamW(net.parameters(), lr=5e-4, weight_decay=0, capturable=True)
+        l_before = ops.LAUNCHES
+        gstep = GraphedTrainStep(net, loss_fn, gopt, dev_x[0], dev_t[0], warmup=2)
+        captured = (ops.LAUNCHES - l_before) // 3  # two warm-up steps + the captured one
+        for i in range(3):
+            gstep(dev_x[i % nbuf], dev_t[i % nbuf])
+        barrier()
+        e0.record()
+        h0 = time.perf_counter()
+        for i in range(args.steps):
+            gloss = gstep(dev_x[i % nbuf], dev_t[i % nbuf])
+        ghost_ms = (time.perf_counter() - h0) * 1e3 / args.steps
+        e1.record()
+        barrier()
+        gms = e0.elapsed_time(e1) / args.steps
+        graph_info = {"value": B / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms, "host_ms_per_step": round(ghost_ms, 3),
+                      "kernels_in_graph": int(captured), "loss": gloss.item(),
+                      "what": "zero_grad + forward + loss + backward + AdamW captured once (GraphedTrainStep), replayed per step; "
+                              "inputs copied device-to-device into the graph's static buffers inside the timed region"}
 
     # ---- end to end: HOST inputs through the library's own input stage (camvid_b200.data.DevicePrefetcher): uint8 HWC
     # images + uint8 masks in pageable memory, as cv2 / the dataset yield them -> pinned ring -> side-stream H2D ->
@@ -460,7 +488,8 @@ def run_b200(args):
            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic", "config": workload_config(args), "e2e": e2e,
-           "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks,
+           "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+           "host_enqueue_ms_per_step": round(host_ms, 3), "graph_replay": graph_info, "clocks": clocks,
            "loss": last_loss, "conv_gflop_per_image": round(flops_img / 1e9, 2),
            "conv_tensor_util_end_to_end": round(value / world * flops_img / 1e12 / pk["tf_sustained"], 4),
            "roofline": roofline, "roofline_wgrad": roofline_wgrad, "kernels": kernels, "diagnostics": diagnostics}

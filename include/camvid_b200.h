@@ -150,6 +150,14 @@ CVB_API int cvb_adamw_chunk_elems(void);
  * step = the 1-based step count of this update (bias corrections 1 - beta^step). */
 CVB_API int cvb_adamw_step(const cvb_adamw_entry* table, const int32_t* chunks, int n_chunks, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int64_t step, void* stream);
+/* The same update for use inside a CUDA graph (kernel arguments are frozen at capture; lr under OneCycleLR,
+ * train.py:102-104,134, and the bias corrections change every step): the per-step scalar factors are computed on the
+ * host by cvb_adamw_factors into 8 floats, copied by the caller to `factors_dev` (stream-ordered, outside the graph)
+ * and read by the kernel from device memory. */
+CVB_API int cvb_adamw_factors(float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                      float* factors_host);
+CVB_API int cvb_adamw_step_dev(const cvb_adamw_entry* table, const int32_t* chunks, int n_chunks, const float* factors_dev,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (+ReLU) in training mode (nn.BatchNorm2d + nn.ReLU: models/unet.py:12-13, models/segnet.py:9-10).

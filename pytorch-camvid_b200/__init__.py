@@ -9,6 +9,8 @@ Layout (mirrors the reference's own module tree for the hot path, see SURVEY.md 
     legacy/metrics.py                  Metrics
     nn.py                              CrossEntropyLoss drop-in on the fused loss kernel
     optim.py                           AdamW drop-in: one fused multi-tensor launch per step
+    data.py                            host -> device input stage: pinned ring + ToTensor / Normalize on the GPU
+    graph.py                           whole training step as one CUDA graph
     engine.py                          execution plans (buffers, kernel sequences) behind the modules
     parallel.py                        data-parallel gradient all-reduce (NCCL, side stream)
     ops.py / _lib.py                   operator layer over the C ABI (include/camvid_b200.h)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "cvb_conv3x3_fprop_fuses_bwd_stats": (_I, [View, View, _I]),
     "cvb_adamw_chunk_elems": (_I, []),
     "cvb_adamw_step": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _L, _P]),
+    "cvb_adamw_factors": (_I, [_F, _F, _F, _F, _F, _L, _P]),
+    "cvb_adamw_step_dev": (_I, [_P, _P, _I, _P, _P]),
     "cvb_conv3x3_wgrad_workspace_bytes": (_L, [View, View, _I]),
     "cvb_conv3x3_wgrad": (_I, [View, View, _I, _P, _I, _I, _P, _L, _P]),
     "cvb_bn_stats": (_I, [View, _P, _I, _P]),

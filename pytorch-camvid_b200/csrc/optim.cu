@@ -14,10 +14,10 @@ namespace cvb {
 constexpr int kOptThreads = 256;
 constexpr int kOptChunk = 16384;  // elements per block
 
-__global__ void __launch_bounds__(kOptThreads) adamw_kernel(const cvb_adamw_entry* __restrict__ table,
-                                                            const int2* __restrict__ chunks, float decay, float b1c,
-                                                            float b2, float b2c, float step_size, float inv_bc2_sqrt,
-                                                            float eps) {
+// one block = one chunk of one tensor
+__device__ __forceinline__ void adamw_chunk(const cvb_adamw_entry* __restrict__ table, const int2* __restrict__ chunks,
+                                            float decay, float b1c, float b2, float b2c, float step_size,
+                                            float inv_bc2_sqrt, float eps) {
   const int2 ck = chunks[blockIdx.x];  // (tensor index, chunk index within the tensor)
   const cvb_adamw_entry e = table[ck.x];
   const long long begin = 1LL * ck.y * kOptChunk;
@@ -56,6 +56,39 @@ __global__ void __launch_bounds__(kOptThreads) adamw_kernel(const cvb_adamw_entr
   }
 }
 
+__global__ void __launch_bounds__(kOptThreads) adamw_kernel(const cvb_adamw_entry* __restrict__ table,
+                                                            const int2* __restrict__ chunks, float decay, float b1c,
+                                                            float b2, float b2c, float step_size, float inv_bc2_sqrt,
+                                                            float eps) {
+  adamw_chunk(table, chunks, decay, b1c, b2, b2c, step_size, inv_bc2_sqrt, eps);
+}
+
+// The seven scalar factors read from DEVICE memory: what a CUDA graph needs, whose kernel arguments are frozen at
+// capture while lr (OneCycleLR) and the bias corrections change every step.
+__global__ void __launch_bounds__(kOptThreads) adamw_dev_kernel(const cvb_adamw_entry* __restrict__ table,
+                                                                const int2* __restrict__ chunks,
+                                                                const float* __restrict__ f) {
+  adamw_chunk(table, chunks, __ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5), __ldg(f + 6));
+}
+
+// scalar factors of one step, in double like torch computes them on the host for python-float hyper-parameters
+static int adamw_factors(float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float* f) {
+  CVB_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+              CVB_ERR_INVALID_ARG, "adamw: bad hyper-parameters (step %lld, betas %g %g, eps %g)", (long long)step,
+              beta1, beta2, eps);
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  f[0] = static_cast<float>(1.0 - static_cast<double>(lr) * static_cast<double>(weight_decay));  // decay
+  f[1] = 1.f - beta1;
+  f[2] = beta2;
+  f[3] = 1.f - beta2;
+  f[4] = static_cast<float>(static_cast<double>(lr) / bc1);  // step size
+  f[5] = static_cast<float>(1.0 / sqrt(bc2));
+  f[6] = eps;
+  f[7] = 0.f;
+  return CVB_OK;
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -65,17 +98,26 @@ extern "C" int cvb_adamw_chunk_elems(void) { return kOptChunk; }
 extern "C" int cvb_adamw_step(const cvb_adamw_entry* table, const int32_t* chunks, int n_chunks, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int64_t step, void* stream) {
   CVB_REQUIRE(table && chunks && n_chunks > 0, CVB_ERR_INVALID_ARG, "adamw_step: empty table");
-  CVB_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
-              CVB_ERR_INVALID_ARG, "adamw_step: bad hyper-parameters (step %lld, betas %g %g, eps %g)",
-              (long long)step, beta1, beta2, eps);
-  // scalar factors in double, like torch computes them on the host for python-float hyper-parameters
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
-  const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
-  const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * static_cast<double>(weight_decay));
+  float f[8];
+  int rc = adamw_factors(lr, beta1, beta2, eps, weight_decay, step, f);
+  if (rc) return rc;
   adamw_kernel<<<n_chunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      table, reinterpret_cast<const int2*>(chunks), decay, 1.f - beta1, beta2, 1.f - beta2, step_size, inv_bc2_sqrt, eps);
+      table, reinterpret_cast<const int2*>(chunks), f[0], f[1], f[2], f[3], f[4], f[5], f[6]);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_adamw_factors(float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                                 float* factors_host) {
+  CVB_REQUIRE(factors_host, CVB_ERR_INVALID_ARG, "adamw_factors: null pointer");
+  return adamw_factors(lr, beta1, beta2, eps, weight_decay, step, factors_host);
+}
+
+extern "C" int cvb_adamw_step_dev(const cvb_adamw_entry* table, const int32_t* chunks, int n_chunks,
+                                  const float* factors_dev, void* stream) {
+  CVB_REQUIRE(table && chunks && n_chunks > 0 && factors_dev, CVB_ERR_INVALID_ARG, "adamw_step_dev: null pointer / empty table");
+  adamw_dev_kernel<<<n_chunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, reinterpret_cast<const int2*>(chunks), factors_dev);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -251,6 +251,8 @@ class Plan:
         """Refreshes the bf16 GEMM operands of every block whose fp32 weight changed (the optimizer bumps the version
         every step): all 3x3 layers in one launch, the im2col'd first layer separately."""
         stale = [b for b in self.blocks if b._weight_key() != b.wf_version]
+        if torch.cuda.is_current_stream_capturing():
+            stale = list(self.blocks)  # a captured step re-packs on every replay: its optimizer moves the weights
         if not stale:
             return
         batch = [b for b in stale if b.taps == 9]
@@ -289,6 +291,11 @@ class Plan:
         t = [b.bn.num_batches_tracked for b in self.blocks if b.bn.num_batches_tracked is not None]
         if t:
             torch._foreach_add_(t, 1)
+        # bn_finalize updated the running statistics through raw pointers: bump their versions like an in-place op
+        # would (the eval-mode fold of BatchNorm into the conv epilogue is cached on them)
+        stats = [s_ for b in self.blocks for s_ in (b.bn.running_mean, b.bn.running_var) if s_ is not None]
+        if stats:
+            torch.autograd.graph.increment_version(stats)
 
     def _begin_backward(self):
         """Flat fp32 gradient buffer of this pass; under data parallelism its ranges are all-reduced as they fill."""
@@ -763,6 +770,15 @@ block_forward_op.register_autograd(_block_backward, setup_context=_block_setup_c
 # used geometries evicted
 PLANS_PER_SHAPE = int(os.environ.get("CVB_PLANS_PER_SHAPE", "2"))  # forwards of one shape that may await their backward
 MAX_SHAPES = int(os.environ.get("CVB_MAX_SHAPES", "4"))            # input geometries kept per module
+
+
+def touch_running_stats(module):
+    """Marks every BatchNorm running statistic of a module as modified (a CUDA-graph replay updates them through raw
+    pointers without torch noticing)."""
+    stats = [b for m in module.modules() if isinstance(m, torch.nn.BatchNorm2d)
+             for b in (m.running_mean, m.running_var) if b is not None]
+    if stats:
+        torch.autograd.graph.increment_version(stats)
 
 
 def plans_of(module):

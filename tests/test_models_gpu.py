@@ -427,6 +427,52 @@ def test_packed_weights_follow_the_optimizer(cvb, cuda, fused_optimizer):
     assert rel_err(logits1, logits0.detach()) > 1e-2  # lr 1e-2 on every conv weight: the output must move
 
 
+def test_graphed_train_step_equals_eager_steps(cvb, cuda):
+    """camvid_b200.graph.GraphedTrainStep: the whole step as one CUDA graph. Building it leaves parameters, running
+    statistics and optimizer state untouched; N replays on N batches then equal N eager steps with the same optimizer --
+    bit for bit (deterministic kernels, same launch sequence) -- including OneCycleLR changing lr / beta1 every step
+    (train.py:102-104,134) and an eager eval forward afterwards seeing the updated weights."""
+    from camvid_b200.graph import GraphedTrainStep
+    from camvid_b200.optim import AdamW
+    cutils, cnn = cvb
+    torch.manual_seed(7)
+    sd = {k: v.clone() for k, v in cutils.get_model("unet", 3, 12).state_dict().items()}
+    batches = [O.synth_batch(2, 48, 64, seed=20 + i) for i in range(3)]
+    batches = [(x.to(cuda), t.to(cuda)) for x, t in batches]
+    results = []
+    for graphed in (False, True):
+        net = _build(cvb, "unet", sd, cuda).train()
+        opt = AdamW(net.parameters(), lr=5e-4, weight_decay=1e-2, capturable=True)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=5e-4, steps_per_epoch=3, epochs=2)
+        loss_fn = cnn.CrossEntropyLoss()
+        if graphed:
+            step = GraphedTrainStep(net, loss_fn, opt, *batches[0])
+            for k, v in net.state_dict().items():
+                assert torch.equal(v.cpu(), sd[k]), k  # construction (warm-up + capture) changed nothing
+            assert all(float(st["step"]) == 0.0 for st in opt.state.values())
+        losses = []
+        for x, t in batches:
+            if graphed:
+                losses.append(step(x, t).item())
+            else:
+                opt.zero_grad(set_to_none=True)
+                loss = loss_fn(net(x), t)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+            sched.step()
+        net.eval()
+        with torch.no_grad():
+            ev = net(batches[0][0]).clone()
+        results.append((losses, {k: v.clone() for k, v in net.state_dict().items()}, ev))
+    (l_e, sd_e, ev_e), (l_g, sd_g, ev_g) = results
+    assert l_e == l_g, (l_e, l_g)
+    for k in sd_e:
+        assert torch.equal(sd_e[k], sd_g[k]), k
+    assert torch.equal(ev_e, ev_g)
+    assert l_e[2] != l_e[0]
+
+
 def test_eval_metrics_pipeline(cvb, cuda):
     """eval.py:50-72 / train.py:180-197 on the device: logits -> argmax -> mean_iou + Metrics, equal to the oracle's
     metric functions applied to the same predictions (integer counts: bit-exact)."""
