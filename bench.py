@@ -305,6 +305,7 @@ def run_b200(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.LAUNCHES - l0) // args.steps
     last_loss = loss.item()
+    del loss  # (an old loss keeps its autograd graph, and with it AccumulateGrad nodes bound to this stream, alive)
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- the same step as one CUDA graph replay (optional)

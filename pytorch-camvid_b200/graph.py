@@ -14,6 +14,10 @@ device memory and refreshed by `optimizer.advance()` right before each replay; t
 from the fp32 weights inside the graph.
 
 Not captured (stays eager): data-parallel runs (the NCCL reducer), eval-mode forwards.
+
+Build it while no earlier loss / output of the network is alive: an old autograd graph keeps the parameters'
+AccumulateGrad nodes bound to the stream it ran on, and a capture cannot make that stream wait on the capturing one
+(torch's own rule for whole-network capture; the constructor turns the CUDA error into this hint).
 """
 import torch
 
@@ -48,8 +52,16 @@ class GraphedTrainStep:
             self._restore(saved)
             optimizer.zero_grad(set_to_none=True)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.loss = self._eager_step()
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._eager_step()
+            except RuntimeError as e:
+                if "capturing" in str(e) or "capture" in str(e):
+                    raise RuntimeError("GraphedTrainStep: the capture was invalidated. The usual cause is a loss / logits "
+                                       "tensor of an earlier eager step that is still alive (its autograd graph pins the "
+                                       "parameters' AccumulateGrad nodes to the default stream): `del loss` before "
+                                       "building the graph. Original error: " + str(e)) from e
+                raise
         self.launches_per_replay = None
 
     def _eager_step(self):
