@@ -203,8 +203,8 @@ CVB_API int cvb_maxpool2x2_bwd(cvb_view dout, const uint8_t* code, cvb_view x_or
 /* cvb_maxpool2x2_bwd fused with cvb_bn_relu_bwd_reduce of the block whose activation was pooled (cross-layer fusion,
  * producer side): writes dx exactly as cvb_maxpool2x2_bwd does and, in the same pass, partials fp32 [rows][2][dx.c] of
  * (sum g, sum g*y), g = dx * [y*scale+shift > 0], taken from the bf16 values it stores (bit-identical to running the
- * two kernels). y = that block's raw conv output (same shape as dx). code == NULL: the argmax is recomputed from
- * relu(y*scale+shift) rounded to bf16 as the forward stored it (UNet keeps no codes). Grid = rows blocks. */
+ * two kernels). y = that block's raw conv output (same shape as dx); code = the window codes the forward wrote
+ * (required). Grid = rows blocks. */
 CVB_API int cvb_maxpool2x2_bwd_bn_reduce(cvb_view dout, const uint8_t* code, cvb_view y, const float* scale,
                                  const float* shift, cvb_view dx, int accumulate, float* partials, int rows,
                                  void* stream);

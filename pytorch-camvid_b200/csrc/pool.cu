@@ -187,13 +187,14 @@ __global__ void __launch_bounds__(kThreads) pool_gather_kernel(View dout, View d
 // MaxPool backward FUSED with the BatchNorm+ReLU backward reduction of the block whose activation was pooled (SURVEY
 // section 8(f) rank 1, producer side): the kernel that last writes `da` -- the gradient w.r.t. that block's activation -- also
 // emits the per-channel sums (g, g*y) with g = da * [y*scale+shift > 0] that cvb_bn_relu_bwd_reduce would otherwise
-// re-read da and y from HBM for. The raw conv output y is needed for the reduction anyway, so with RECOMPUTE the
-// argmax is rebuilt from relu(bn(y)) (rounded to bf16 exactly as the forward stored it) instead of reading the
-// activation: per element 6.5 B (y, da in/out, dout/4) instead of 6.5 + 4.
-// Mapping as in bn_reduce_kernel: a thread keeps ONE 8-channel group, blocks stride over windows, one partial row per
-// block. Sums are taken from the bf16-rounded da that is stored: bit-identical to the unfused pair of kernels.
-template <bool ACCUM, bool RECOMPUTE>
-__global__ void __launch_bounds__(kThreads, 2) pool_bwd_bn_reduce_kernel(View dout, View y, View dx,
+// re-read da and y from HBM for: per element 6.75 B (y, da in/out, dout/4, code/4) instead of 6.5 + 4.
+// Built like bn_reduce_kernel, one thread = 8 channels of one PIXEL (not of a window: a window-per-thread version
+// needed 128+ registers and ran at 3.2 TB/s, slower than the two kernels it replaced): the pixel looks up its window's
+// code and pooled gradient (read by its three neighbours too: L1 / L2 hits). A thread keeps one channel group, blocks
+// stride over pixels, one partial row per block. Sums are taken from the bf16-rounded da that is stored, so the result
+// is bit-identical to the unfused pair.
+template <bool ACCUM>
+__global__ void __launch_bounds__(kThreads, 3) pool_bwd_bn_reduce_kernel(View dout, View y, View dx,
                                                                        const uint8_t* __restrict__ code,
                                                                        const float* __restrict__ scale,
                                                                        const float* __restrict__ shift,
@@ -203,74 +204,57 @@ __global__ void __launch_bounds__(kThreads, 2) pool_bwd_bn_reduce_kernel(View do
   const int ppb = kThreads / CV;
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
-  const int HO = (dx.h + 1) >> 1, WO = (dx.w + 1) >> 1;
-  const unsigned nwin = 1u * dx.n * HO * WO;
+  const unsigned npix = 1u * dx.n * dx.h * dx.w;
   float sc[8], sh[8], s1[8], s2[8];
   ld8f(scale + cv * 8, sc);
   ld8f(shift + cv * 8, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  for (unsigned win = blockIdx.x * ppb + pl; win < nwin; win += gridDim.x * ppb) {
-    unsigned t = win;
-    const int wo = static_cast<int>(t % WO);
-    t /= WO;
-    const int ho = static_cast<int>(t % HO);
-    const int n = static_cast<int>(t / HO);
-    const int h0 = 2 * ho, w0 = 2 * wo;
-    const bool hv = (h0 + 1) < dx.h, wv = (w0 + 1) < dx.w;
-    const bool full = hv && wv && ho < dout.h && wo < dout.w;
-    // every load of the window first
-    uint4 uy[4], ud[4];
-    uint4 ug = make_uint4(0u, 0u, 0u, 0u);
-    uint2 uc = make_uint2(0u, 0u);
+  const unsigned step = gridDim.x * ppb;
+  for (unsigned pix0 = blockIdx.x * ppb + pl; pix0 < npix; pix0 += 2 * step) {
+    // two pixels per iteration, every load issued before the arithmetic
+    uint4 uy[2], ud[2], ug[2];
+    unsigned kk[2];  // position of the pixel in its window
+    uint2 uc[2];
+    bool live[2], full[2];
+    __nv_bfloat16* dst[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool valid = ((k >> 1) == 0 || hv) && ((k & 1) == 0 || wv);
-      uy[k] = ud[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (valid) {
-        uy[k] = ldg16(y.p + voff(y, n, h0 + (k >> 1), w0 + (k & 1)) + cv * 8);
-        if (ACCUM) ud[k] = *reinterpret_cast<const uint4*>(dx.p + voff(dx, n, h0 + (k >> 1), w0 + (k & 1)) + cv * 8);
+    for (int q = 0; q < 2; ++q) {
+      const unsigned pix = pix0 + q * step;
+      live[q] = pix < npix;
+      full[q] = false;
+      uy[q] = ud[q] = ug[q] = make_uint4(0u, 0u, 0u, 0u);
+      uc[q] = make_uint2(0u, 0u);
+      if (!live[q]) continue;
+      unsigned t = pix;
+      const int w = static_cast<int>(t % dx.w);
+      t /= dx.w;
+      const int h = static_cast<int>(t % dx.h);
+      const int n = static_cast<int>(t / dx.h);
+      const int ho = h >> 1, wo = w >> 1;
+      kk[q] = static_cast<unsigned>((h & 1) * 2 + (w & 1));
+      full[q] = ho < dout.h && wo < dout.w;  // odd last row / column: no window, the gradient passes through unchanged
+      dst[q] = dx.p + voff(dx, n, h, w) + cv * 8;
+      uy[q] = ldg16(y.p + voff(y, n, h, w) + cv * 8);
+      if (ACCUM) ud[q] = *reinterpret_cast<const uint4*>(dst[q]);
+      if (full[q]) {
+        ug[q] = ldg16(dout.p + voff(dout, n, ho, wo) + cv * 8);
+        uc[q] = __ldg(reinterpret_cast<const uint2*>(code + ((1LL * n * dout.h + ho) * dout.w + wo) * dx.c + cv * 8));
       }
     }
-    if (full) {
-      ug = ldg16(dout.p + voff(dout, n, ho, wo) + cv * 8);
-      if (!RECOMPUTE) uc = __ldg(reinterpret_cast<const uint2*>(code + ((1LL * n * dout.h + ho) * dout.w + wo) * dx.c + cv * 8));
-    }
-    // (operands stay packed between the two phases: registers decide the occupancy of this kernel)
-    float g[8];
-    uint32_t cd[8];
-    unpack8(ug, g);
-    if (RECOMPUTE) {
-      float best[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {  // torch's scan: (0,0),(0,1),(1,0),(1,1); take val if val > max or val is NaN
-        float a[8];
-        unpack8(uy[k], a);
+    for (int q = 0; q < 2; ++q) {
+      if (!live[q]) continue;
+      float o[8], g[8], fy[8];
+      uint32_t cd[8];
+      unpack8(ud[q], o);  // zeros unless ACCUM
+      unpack8(ug[q], g);
+      unpack8(uy[q], fy);
+      unpack_code(uc[q], cd);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f);
-        unpack8(pack8(a), a);  // the activation as the forward stored it (bf16): same ties, same codes
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (k == 0 || a[j] > best[j] || a[j] != a[j]) {
-            best[j] = a[j];
-            cd[j] = k;
-          }
-        }
-      }
-    } else {
-      unpack_code(uc, cd);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool valid = ((k >> 1) == 0 || hv) && ((k & 1) == 0 || wv);
-      if (!valid) continue;
-      float o[8], fy[8];
-      unpack8(ud[k], o);  // zeros unless ACCUM
-      unpack8(uy[k], fy);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (full && cd[j] == static_cast<uint32_t>(k)) ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) o[j] += (full[q] && cd[j] == kk[q]) ? g[j] : 0.f;
       const uint4 pk = pack8(o);
-      if (!ACCUM || full) stg16(dx.p + voff(dx, n, h0 + (k >> 1), w0 + (k & 1)) + cv * 8, pk);
+      if (!ACCUM || full[q]) stg16(dst[q], pk);
       unpack8(pk, o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -403,20 +387,14 @@ extern "C" int cvb_maxpool2x2_bwd_bn_reduce(cvb_view dout, const uint8_t* code, 
   const int CV = dx.c / 8;
   CVB_REQUIRE(CV <= kThreads && (kThreads % CV) == 0, CVB_ERR_UNSUPPORTED,
               "maxpool_bwd_bn_reduce: channels %d must divide %d", dx.c, kThreads * 8);
-  CVB_REQUIRE(1LL * dx.n * ((dx.h + 1) / 2) * ((dx.w + 1) / 2) < (1LL << 31), CVB_ERR_UNSUPPORTED,
+  CVB_REQUIRE(1LL * dx.n * dx.h * dx.w < (1LL << 31), CVB_ERR_UNSUPPORTED,
               "maxpool_bwd_bn_reduce: view too large for 32-bit indexing");
+  CVB_REQUIRE(code, CVB_ERR_INVALID_ARG, "maxpool_bwd_bn_reduce: null index codes (cvb_bn_relu_maxpool2x2_fwd writes them)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (code) {
-    if (accumulate)
-      pool_bwd_bn_reduce_kernel<true, false><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
-    else
-      pool_bwd_bn_reduce_kernel<false, false><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
-  } else {
-    if (accumulate)
-      pool_bwd_bn_reduce_kernel<true, true><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), nullptr, scale, shift, partials);
-    else
-      pool_bwd_bn_reduce_kernel<false, true><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), nullptr, scale, shift, partials);
-  }
+  if (accumulate)
+    pool_bwd_bn_reduce_kernel<true><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
+  else
+    pool_bwd_bn_reduce_kernel<false><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -347,7 +347,7 @@ class UNetPlan(Plan):
         downs = [m.down1, m.down2, m.down3, m.down4, m.down5]
         self.enc = []
         x = self.cols
-        self.pooled, self.dpooled, self.enc_mid, self.d_enc_mid = [], [], [], []
+        self.pooled, self.dpooled, self.enc_mid, self.d_enc_mid, self.codes = [], [], [], [], []
         for l in range(5):
             mid = self.buf(hs[l], ws[l], ch[l])
             self.enc_mid.append(mid)
@@ -358,6 +358,8 @@ class UNetPlan(Plan):
                 pooled = self.buf(hs[l + 1], ws[l + 1], ch[l])
                 self.pooled.append(pooled)
                 self.dpooled.append(torch.empty_like(pooled))
+                # window codes (1 byte per pooled element): the fused pool-backward + BatchNorm-reduce kernel reads them
+                self.codes.append(torch.empty(pooled.shape, dtype=torch.uint8, device=device) if FUSE_POOL_BWD_REDUCE else None)
             else:
                 out = self.buf(hs[l], ws[l], ch[l])
                 self.bott, self.dbott = out, torch.empty_like(out)
@@ -400,7 +402,7 @@ class UNetPlan(Plan):
             if train:
                 b0.forward_train()
                 if l < 4:
-                    b1.forward_train(pool_out=self.pooled[l])
+                    b1.forward_train(pool_out=self.pooled[l], code=self.codes[l])
                 else:
                     b1.forward_train()
             else:
@@ -443,9 +445,10 @@ class UNetPlan(Plan):
                 ch = self.cat[l].shape[3] // 2
                 da = self.dcat[l][..., ch:]
                 # encoder activation feeds both the skip (already in dcat) and the pool: add the pool path
-                if FUSE_POOL_BWD_REDUCE and b1.ce == da.shape[3]:
+                if self.codes[l] is not None and b1.ce == da.shape[3]:
                     ops.maxpool2x2_bwd_bn_reduce(self.dpooled[l], da, b1.y_e, b1.vec[2], b1.vec[3],
-                                                 self.parts_view(b1.ce), self.reduce_rows, accumulate=True)
+                                                 self.parts_view(b1.ce), self.reduce_rows, code=self.codes[l],
+                                                 accumulate=True)
                     pooled_ready = self.reduce_rows
                 else:
                     ops.maxpool2x2_bwd(self.dpooled[l], da, x=b1.a, accumulate=True)

@@ -370,7 +370,8 @@ def test_bilinear2x(ops, cuda, n, h, w, c):
 def test_maxpool_bwd_fused_with_bn_reduce_is_bit_identical(ops, cuda, n, h, w, c, mode):
     """cvb_maxpool2x2_bwd_bn_reduce (cross-layer fusion, producer side) against the two kernels it replaces on the same
     buffers: dx bit-identical, reduction partials summing to the same (sum g, sum g*y) up to fp32 summation order.
-    unet: accumulate into the skip gradient, argmax recomputed from relu(bn(y)); segnet: scatter by the stored codes."""
+    unet: accumulate into the skip gradient (the unfused reference recomputes the argmax from the activation, the fused
+    kernel reads the forward's codes); segnet: plain scatter by the stored codes."""
     torch.manual_seed(33)
     y = _rand((n, h, w, c), cuda, 70).to(torch.bfloat16)
     scale = (torch.rand(c, device=cuda) + 0.5) * torch.where(torch.rand(c, device=cuda) < 0.2, -1.0, 1.0)  # some gamma < 0
@@ -391,7 +392,7 @@ def test_maxpool_bwd_fused_with_bn_reduce_is_bit_identical(ops, cuda, n, h, w, c
     # fused
     dx = skip.clone() if acc else torch.full_like(skip, 7.0)
     parts = torch.full((rows, 2, c), float("nan"), device=cuda)
-    ops.maxpool2x2_bwd_bn_reduce(dout, dx, y, scale, shift, parts, rows, code=None if acc else code, accumulate=acc)
+    ops.maxpool2x2_bwd_bn_reduce(dout, dx, y, scale, shift, parts, rows, code=code, accumulate=acc)
     assert torch.equal(dx, dx_ref)
     s, s_ref = parts.double().sum(0), parts_ref.double().sum(0)
     assert torch.isfinite(s).all()

@@ -51,9 +51,10 @@ timeit("bn_relu_bwd_apply", lambda: ops.bn_relu_bwd_apply(da, y, scale, shift, c
 timeit("bn_relu_maxpool", lambda: ops.bn_relu_maxpool2x2(y, scale, shift, a, pooled), 4 * E + E // 2)
 timeit("maxpool_bwd(recompute)", lambda: ops.maxpool2x2_bwd(pooled, dy, x=a, accumulate=True), 6 * E + E // 2)
 da2 = da.clone()
+code8 = torch.randint(0, 4, pooled.shape, dtype=torch.uint8, device=dev)
 timeit("pool_bwd+reduce (2 kernels)", lambda: (ops.maxpool2x2_bwd(pooled, da2, x=a, accumulate=True),
                                               ops.bn_relu_bwd_reduce(da2, y, scale, shift, parts, rows)), 10 * E + E // 2)
-timeit("pool_bwd_bn_reduce fused", lambda: ops.maxpool2x2_bwd_bn_reduce(pooled, da2, y, scale, shift, parts, rows, accumulate=True),
+timeit("pool_bwd_bn_reduce fused", lambda: ops.maxpool2x2_bwd_bn_reduce(pooled, da2, y, scale, shift, parts, rows, code=code8, accumulate=True),
        6 * E + E // 2)
 if up is not None:
     timeit("bilinear2x_fwd", lambda: ops.bilinear2x(y, up), 2 * E + 8 * E)
