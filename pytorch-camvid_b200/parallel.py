@@ -13,14 +13,24 @@ buckets only once, right before autograd hands the gradients to the optimizer.
 BatchNorm uses per-replica batch statistics (what the reference's DP and torch DDP do). Gradients are averaged, which
 equals the gradient of the global-mean loss when shards are equal-sized.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# Measurement knobs (DESIGN.md section 6): CVB_BUCKET_MB sets the bucket size (a value larger than the gradient buffer =
+# one all-reduce after the backward pass, nothing overlapped); CVB_DP_PAYLOAD=bf16 halves the bytes on the wire (the
+# bucket is converted on the side stream; mean of bf16-rounded gradients); CVB_DP_PAYLOAD=none skips the exchange
+# entirely (replicas drift apart: only for timing the compute without any communication).
+_BUCKET_MB = float(os.environ.get("CVB_BUCKET_MB", "25"))
+_PAYLOAD = os.environ.get("CVB_DP_PAYLOAD", "fp32")
 
 
 class GradReducer:
     """Bucketed mean all-reduce over a flat gradient buffer whose ranges become ready front to back."""
 
-    def __init__(self, process_group=None, bucket_mb=25.0):
+    def __init__(self, process_group=None, bucket_mb=None):
+        bucket_mb = _BUCKET_MB if bucket_mb is None else bucket_mb
         if not dist.is_initialized():
             raise RuntimeError("camvid_b200.parallel: torch.distributed is not initialised")
         self.group = process_group
@@ -54,7 +64,7 @@ class GradReducer:
         chunk = self.flat[self.lo:self.hi]
         self.lo = self.hi
         self.buckets_launched += 1
-        if self.world == 1:
+        if self.world == 1 or _PAYLOAD == "none":
             return
         avg = self.backend == "nccl"
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
@@ -63,7 +73,13 @@ class GradReducer:
             if also_wait is not None:
                 self.side.wait_stream(also_wait)
             with torch.cuda.stream(self.side):
-                work = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
+                if _PAYLOAD == "bf16":
+                    half = chunk.to(torch.bfloat16)
+                    work = dist.all_reduce(half, op=op, group=self.group, async_op=True)
+                    work.wait()
+                    chunk.copy_(half)
+                else:
+                    work = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
         else:
             work = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
         self.works.append((work, chunk, avg))
@@ -81,7 +97,7 @@ class GradReducer:
         self.flat = None
 
 
-def data_parallel(module, process_group=None, bucket_mb=25.0, broadcast=True):
+def data_parallel(module, process_group=None, bucket_mb=None, broadcast=True):
     """Marks a drop-in UNet / SegNet for data-parallel training and returns it (the module API is unchanged).
 
     broadcast=True copies rank 0's parameters and buffers to every rank first, so replicas start identical even when
