@@ -88,32 +88,43 @@ __device__ __forceinline__ float tap_weight(float scale, int dst, int in, int ta
 
 // Output positions whose stencil touches input position `target`, with their weights (at most 6 for a x2 upsample:
 // sources lie in the open interval (target-1, target+1), 2/scale wide).
-__device__ __forceinline__ int gather_taps(float scale, float inv, int in, int out, int target, int (&idx)[6],
-                                           float (&wgt)[6]) {
+template <int NT>
+__device__ __forceinline__ int gather_taps(float scale, float inv, int in, int out, int target, int (&idx)[NT],
+                                           float (&wgt)[NT]) {
   const int lo = max(0, static_cast<int>(floorf((target - 1) * inv)) - 1);
   const int hi = min(out - 1, static_cast<int>(ceilf((target + 1) * inv)) + 1);
   int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    idx[k] = 0;
+    wgt[k] = 0.f;
+  }
   for (int o = lo; o <= hi; ++o) {
     const float w = tap_weight(scale, o, in, target);
-    if (w != 0.f && cnt < 6) {
-      idx[cnt] = o;
-      wgt[cnt] = w;
+    if (w != 0.f) {
+#pragma unroll
+      for (int k = 0; k < NT; ++k)  // (static indexing keeps idx / wgt in registers)
+        if (k == cnt) {
+          idx[k] = o;
+          wgt[k] = w;
+        }
       ++cnt;
     }
   }
+  const int first = idx[0];
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
-    if (k >= cnt) {
-      idx[k] = idx[0];
-      wgt[k] = 0.f;
-    }
-  return cnt;
+  for (int k = 0; k < NT; ++k)
+    if (k >= cnt) idx[k] = first;  // unused slots re-read the first tap with weight 0
+  return cnt < NT ? cnt : NT;
 }
 
 // Backward, separable: one thread = one 8-channel vector of one input COLUMN and a strip of `rows` input rows. It walks
 // the output rows whose stencils touch the strip; per output row it gathers along x (the <= 6 output columns that touch
 // its input column, found once per thread) and adds the result into two rolling row accumulators (source rows y0 and
 // y0 + 1 of that output row). 4-5 loads per output row instead of 16-25 per input pixel.
+// NT = tap slots along x: 4 is exact for every 2x align_corners upsampling of an input wider than 1 (each input
+// column is touched by 4 output columns, 3 at the edges -- counted on the host, which falls back to 6 slots otherwise).
+template <int NT>
 __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, View dx, float sy, float sx, float isy,
                                                                    float isx, int rows, int strips, int pf) {
   const unsigned CV = static_cast<unsigned>(dx.c) >> 3;
@@ -125,9 +136,9 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, Vie
     t /= dx.w;
     const int s = static_cast<int>(t % strips);
     const int n = static_cast<int>(t / strips);
-    int ox[6];
-    float wx[6];
-    const int nx = gather_taps(sx, isx, dx.w, dout.w, ix, ox, wx);
+    int ox[NT];
+    float wx[NT];
+    const int nx = gather_taps<NT>(sx, isx, dx.w, dout.w, ix, ox, wx);
     const __nv_bfloat16* src = dout.p + n * dout.sn + cv * 8;
     __nv_bfloat16* dst = dx.p + n * dx.sn + ix * dx.sw + cv * 8;
     const int ra = s * rows, rb = min(dx.h, ra + rows);  // owned input rows [ra, rb)
@@ -156,17 +167,17 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, Vie
       if (pf > 0 && oy + pf <= hi) {  // the iterations are dependent (one row of taps in flight per thread): keep `pf`
         const __nv_bfloat16* ahead = rowp + pf * dout.sh;  // further rows of DRAM requests outstanding through L2
 #pragma unroll
-        for (int b = 0; b < 6; ++b)
+        for (int b = 0; b < NT; ++b)
           if (b < nx) prefetch_l2(ahead + ox[b] * dout.sw);
       }
-      uint4 u[6];
+      uint4 u[NT];
 #pragma unroll
-      for (int b = 0; b < 6; ++b) u[b] = b < nx ? ldg16(rowp + ox[b] * dout.sw) : make_uint4(0u, 0u, 0u, 0u);
+      for (int b = 0; b < NT; ++b) u[b] = b < nx ? ldg16(rowp + ox[b] * dout.sw) : make_uint4(0u, 0u, 0u, 0u);
       float g[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
-      for (int b = 0; b < 6; ++b) {
+      for (int b = 0; b < NT; ++b) {
         float v[8];
         unpack8(u[b], v);
 #pragma unroll
@@ -225,6 +236,33 @@ extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   return CVB_OK;
 }
 
+// largest number of output positions whose stencil touches one input position (same fp32 index math as the kernels)
+static int max_adjoint_taps(int in, int out) {
+  const float scale = ac_scale(in, out);
+  int best = 0, run_target = -1, run = 0;
+  // taps of input position t = #{o: i0(o) == t with l0 != 0} + #{o: i1(o) == t != i0(o) with l1 != 0}; both sets are
+  // contiguous in o, so two running counters indexed by position suffice
+  static thread_local int cnt[4096];
+  if (in > 4096) return 6;
+  for (int t = 0; t < in; ++t) cnt[t] = 0;
+  for (int o = 0; o < out; ++o) {
+    const float src = scale * static_cast<float>(o);
+    int i0 = static_cast<int>(src);
+    if (i0 > in - 1) i0 = in - 1;
+    const int i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+    const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
+    if (i1 == i0) {
+      if (l0 + l1 != 0.f) ++cnt[i0];
+    } else {
+      if (l0 != 0.f) ++cnt[i0];
+      if (l1 != 0.f) ++cnt[i1];
+    }
+  }
+  (void)run_target; (void)run;
+  for (int t = 0; t < in; ++t) best = cnt[t] > best ? cnt[t] : best;
+  return best;
+}
+
 extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   int rc = check_view(dout, "bilinear_bwd.dout");
   if (rc) return rc;
@@ -236,7 +274,7 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   float isy = sy > 0.f ? 1.f / sy : static_cast<float>(dout.h), isx = sx > 0.f ? 1.f / sx : static_cast<float>(dout.w);
   CVB_REQUIRE(fits_u32(dout), CVB_ERR_UNSUPPORTED, "bilinear2x_bwd: view too large for 32-bit indexing");
   const int cv = dx.c / 8;
-  const int rows = strip_rows(dx.n, dx.h, dx.w, cv, 8);
+  const int rows = strip_rows(dx.n, dx.h, dx.w, cv, 16);
   const int strips = (dx.h + rows - 1) / rows;
   long long total = 1LL * dx.n * strips * dx.w * cv;
   const int grid = ew_grid(total, kThreads);
@@ -246,8 +284,12 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
     const char* e = getenv("CVB_BILINEAR_SMEM");
     dbg_smem = e ? atoi(e) : 0;
   }
-  bilinear2x_bwd_kernel<<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
-                                                   prefetch_rows());
+  if (max_adjoint_taps(dx.w, dout.w) <= 4)
+    bilinear2x_bwd_kernel<4><<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
+                                                              prefetch_rows());
+  else
+    bilinear2x_bwd_kernel<6><<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
+                                                              prefetch_rows());
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
