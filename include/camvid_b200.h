@@ -283,6 +283,30 @@ CVB_API int cvb_input_stage_u8(const uint8_t* img_u8, int n, int h, int w, int c
                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink / NVSwitch peer memory (the path's one exchange step; reference
+ * precedent: legacy/train_tpu.py:115 `xm.optimizer_step(optimizer)`, the XLA all-reduce of the gradients). One
+ * process per GPU. Every rank allocates its flat fp32 gradient buffer and a flag pad of cvb_comm_flag_words() uint32
+ * (zeroed once) as peer-accessible ("symmetric") memory and exchanges the device pointers; the kernels use no shared
+ * memory and few registers, so they run on the same SMs as the backward pass's convolution kernels.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define CVB_COMM_MAX_WORLD 8     /* ranks: the GPUs of one NVSwitch box */
+#define CVB_COMM_MAX_BUCKETS 64  /* all-reduce calls per step */
+typedef struct {
+  void* const* peer_bufs_host;   /* HOST array [world] of DEVICE pointers: rank p's gradient buffer as mapped in THIS process */
+  void* const* peer_flags_host;  /* HOST array [world] of DEVICE pointers: rank p's flag pad */
+  int32_t rank, world;
+} cvb_comm;
+CVB_API int cvb_comm_flag_words(void);
+/* In place: buf[offset, offset+count) (fp32 elements) := mean over the ranks, on every rank, identical bits everywhere
+ * (rank r reduces slice r in rank order and stores it to all ranks). `bucket` numbers the calls of one step
+ * (0 .. CVB_COMM_MAX_BUCKETS-1, same sequence on every rank), `epoch` the steps (nonzero, increasing). Asynchronous on
+ * `stream`; the results are complete on a stream once cvb_allreduce_wait has run on it. */
+CVB_API int cvb_allreduce_mean_f32(const cvb_comm* comm, int64_t offset, int64_t count, int bucket, uint32_t epoch, int ctas,
+                           void* stream);
+/* Makes `stream` wait until buckets 0 .. n_buckets-1 of `epoch` have arrived from every rank. */
+CVB_API int cvb_allreduce_wait(const cvb_comm* comm, int n_buckets, uint32_t epoch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Utilities
  * ------------------------------------------------------------------------------------------------------------- */
 /* Zero-fills a bf16 view (pad rows of concat buffers). */

@@ -26,6 +26,12 @@ class ConvEpilogue(ctypes.Structure):
                 ("bwd_shift", ctypes.c_void_p), ("bwd_partials", ctypes.c_void_p)]
 
 
+class Comm(ctypes.Structure):
+    """cvb_comm: peer pointers of the symmetric gradient buffer / flag pad."""
+    _fields_ = [("peer_bufs_host", ctypes.POINTER(ctypes.c_void_p)), ("peer_flags_host", ctypes.POINTER(ctypes.c_void_p)),
+                ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+
+
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _L = ctypes.c_int64
@@ -73,6 +79,9 @@ SIGNATURES = {
     "cvb_argmax_confusion_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_argmax_confusion_nhwc_bf16": (_I, [View, _I, _P, _I, _P, _P, _P]),
     "cvb_input_stage_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "cvb_comm_flag_words": (_I, []),
+    "cvb_allreduce_mean_f32": (_I, [_P, _L, _L, _I, ctypes.c_uint32, _I, _P]),
+    "cvb_allreduce_wait": (_I, [_P, _I, ctypes.c_uint32, _P]),
     "cvb_zero_view": (_I, [View, _P]),
 }
 

@@ -1,0 +1,195 @@
+// Gradient all-reduce over NVLink / NVSwitch peer memory (the one exchange step of the data-parallel
+// path; precedent legacy/train_tpu.py:115 `xm.optimizer_step`). One process per GPU; every rank's flat gradient buffer
+// and flag pad live in symmetric memory, so each rank holds device pointers to all peers' copies.
+//
+// Why not NCCL for this: its all-reduce kernels need SM slots of their own (large blocks + shared memory) and cannot
+// co-reside with the persistent 1-CTA-per-SM convolution kernels of the backward pass (~200 KB of shared memory each), so a
+// bucket launched "in the background" waits for a conv kernel to end and then keeps some SMs away from the next one,
+// whose static tile schedule stretches by that delay (measured: +0.5 ms / step at 2 GPUs). This kernel
+// uses NO shared memory, 256 threads and < 48 registers: its CTAs fit beside a convolution CTA on the same SM -- like the
+// BatchNorm passes that already overlap the weight gradients -- and it moves the bytes with plain peer loads / stores.
+//
+// Algorithm per bucket (in place, deterministic, identical bits on every rank):
+//   rank r owns slice r of the bucket. It (1) tells every peer "my copy of this bucket is final" (flag write, release at
+//   system scope), (2) waits for the same message from every peer, (3) for each element of ITS slice loads the value from
+//   all ranks in rank order, sums, scales by 1/world and stores the result into the slice on ALL ranks, (4) after a
+//   system-scope fence its last CTA tells every peer "slice r of this bucket has arrived". cvb_allreduce_wait makes the
+//   consumer stream wait for those messages from all ranks. Slice r is read and written by rank r only, so nothing
+//   races; flags carry the step's epoch (monotone), so they are never reset.
+#include "common.cuh"
+
+namespace cvb {
+
+constexpr int kArThreads = 256;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer data: relaxed system-scope accesses (never served from a non-coherent cache)
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_f4(float* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ld_sys_f1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_f1(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+struct CommDev {
+  float* bufs[CVB_COMM_MAX_WORLD];
+  uint32_t* flags[CVB_COMM_MAX_WORLD];
+  int rank, world;
+};
+
+// flag pad layout (uint32): [0, MAXB*MAXW) = "ready" [bucket][rank]; [MAXB*MAXW, 2*MAXB*MAXW) = "arrived" [bucket][rank];
+// the last word = CTA ticket of the local kernel
+__device__ __forceinline__ int ready_idx(int b, int r) { return b * CVB_COMM_MAX_WORLD + r; }
+__device__ __forceinline__ int done_idx(int b, int r) { return (CVB_COMM_MAX_BUCKETS + b) * CVB_COMM_MAX_WORLD + r; }
+constexpr int kTicketIdx = 2 * CVB_COMM_MAX_BUCKETS * CVB_COMM_MAX_WORLD;
+
+__device__ __forceinline__ long long slice_bound(long long offset, long long count, int k, int world) {
+  if (k <= 0) return offset;
+  if (k >= world) return offset + count;
+  const long long b = offset + count * k / world;
+  const long long a = (b + 3) & ~3LL;  // slices start on 16-byte boundaries of the (16-byte aligned) buffer
+  return a < offset + count ? a : offset + count;
+}
+
+__global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, long long offset, long long count,
+                                                                     int bucket, uint32_t epoch) {
+  uint32_t* my_flags = c.flags[c.rank];
+  // (1) my bucket is final: every kernel that wrote it precedes this one in stream order
+  if (blockIdx.x == 0 && threadIdx.x < c.world) {
+    __threadfence_system();
+    st_release_sys(c.flags[threadIdx.x] + ready_idx(bucket, c.rank), epoch);
+  }
+  // (2) every peer's bucket is final
+  if (threadIdx.x < c.world) {
+    const uint32_t* f = my_flags + ready_idx(bucket, threadIdx.x);
+    while (ld_acquire_sys(f) != epoch) __nanosleep(64);
+  }
+  __syncthreads();
+  // (3) my slice
+  const long long lo = slice_bound(offset, count, c.rank, c.world), hi = slice_bound(offset, count, c.rank + 1, c.world);
+  const float inv = 1.f / static_cast<float>(c.world);
+  const long long v_lo = (lo + 3) & ~3LL, v_hi = hi & ~3LL;  // vector body; a ragged head / tail goes element by element
+  if (v_hi > v_lo) {
+    const long long n4 = (v_hi - v_lo) >> 2;
+    const long long stride = 1LL * gridDim.x * kArThreads;
+    for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += 2 * stride) {
+      const long long e0 = v_lo + 4 * i, e1 = e0 + 4 * stride;
+      const bool two = i + stride < n4;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+      for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {  // rank order: the same sum on every rank, every step
+        if (p >= c.world) break;
+        const float4 v0 = ld_sys_f4(c.bufs[p] + e0);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        if (two) {
+          const float4 v1 = ld_sys_f4(c.bufs[p] + e1);
+          a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        }
+      }
+      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
+      a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
+#pragma unroll
+      for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {
+        if (p >= c.world) break;
+        st_sys_f4(c.bufs[p] + e0, a0);
+        if (two) st_sys_f4(c.bufs[p] + e1, a1);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (long long e = lo + threadIdx.x; e < hi; e += kArThreads) {
+      if (e >= v_lo && e < v_hi) continue;
+      float a = 0.f;
+      for (int p = 0; p < c.world; ++p) a += ld_sys_f1(c.bufs[p] + e);
+      a *= inv;
+      for (int p = 0; p < c.world; ++p) st_sys_f1(c.bufs[p] + e, a);
+    }
+  }
+  // (4) slice r has arrived everywhere
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(my_flags + kTicketIdx, 1u);
+    last = t == gridDim.x - 1;
+    if (last) my_flags[kTicketIdx] = 0u;  // launches of one rank are stream-ordered: the next one starts from 0
+  }
+  __syncthreads();
+  if (last && threadIdx.x < c.world) {
+    __threadfence_system();
+    st_release_sys(c.flags[threadIdx.x] + done_idx(bucket, c.rank), epoch);
+  }
+}
+
+__global__ void allreduce_wait_kernel(CommDev c, int n_buckets, uint32_t epoch) {
+  const uint32_t* my_flags = c.flags[c.rank];
+  for (int i = threadIdx.x; i < n_buckets * c.world; i += blockDim.x) {
+    const uint32_t* f = my_flags + done_idx(i / c.world, i % c.world);
+    while (ld_acquire_sys(f) != epoch) __nanosleep(64);
+  }
+}
+
+static int load_comm(const cvb_comm* comm, CommDev* c) {
+  CVB_REQUIRE(comm && comm->peer_bufs_host && comm->peer_flags_host, CVB_ERR_INVALID_ARG, "allreduce: null communicator");
+  CVB_REQUIRE(comm->world >= 1 && comm->world <= CVB_COMM_MAX_WORLD && comm->rank >= 0 && comm->rank < comm->world,
+              CVB_ERR_INVALID_ARG, "allreduce: rank %d / world %d (max %d ranks)", comm->rank, comm->world, CVB_COMM_MAX_WORLD);
+  for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {
+    c->bufs[p] = p < comm->world ? static_cast<float*>(comm->peer_bufs_host[p]) : nullptr;
+    c->flags[p] = p < comm->world ? static_cast<uint32_t*>(comm->peer_flags_host[p]) : nullptr;
+    if (p < comm->world) {
+      CVB_REQUIRE(c->bufs[p] && c->flags[p], CVB_ERR_INVALID_ARG, "allreduce: null peer pointer for rank %d", p);
+      CVB_REQUIRE((reinterpret_cast<uintptr_t>(c->bufs[p]) & 15) == 0, CVB_ERR_INVALID_ARG, "allreduce: peer buffer not 16-byte aligned");
+    }
+  }
+  c->rank = comm->rank;
+  c->world = comm->world;
+  return CVB_OK;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" int cvb_comm_flag_words(void) { return kTicketIdx + 4; }
+
+extern "C" int cvb_allreduce_mean_f32(const cvb_comm* comm, int64_t offset, int64_t count, int bucket, uint32_t epoch,
+                                      int ctas, void* stream) {
+  CommDev c;
+  int rc = load_comm(comm, &c);
+  if (rc) return rc;
+  CVB_REQUIRE(offset >= 0 && count > 0, CVB_ERR_INVALID_ARG, "allreduce: empty range");
+  CVB_REQUIRE(bucket >= 0 && bucket < CVB_COMM_MAX_BUCKETS && epoch != 0, CVB_ERR_INVALID_ARG,
+              "allreduce: bucket %d (max %d) / epoch %u", bucket, CVB_COMM_MAX_BUCKETS, epoch);
+  if (ctas < 1) ctas = 1;
+  if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
+  allreduce_mean_kernel<<<ctas, kArThreads, 0, static_cast<cudaStream_t>(stream)>>>(c, offset, count, bucket, epoch);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_allreduce_wait(const cvb_comm* comm, int n_buckets, uint32_t epoch, void* stream) {
+  CommDev c;
+  int rc = load_comm(comm, &c);
+  if (rc) return rc;
+  CVB_REQUIRE(n_buckets >= 0 && n_buckets <= CVB_COMM_MAX_BUCKETS && epoch != 0, CVB_ERR_INVALID_ARG,
+              "allreduce_wait: %d buckets (max %d) / epoch %u", n_buckets, CVB_COMM_MAX_BUCKETS, epoch);
+  if (n_buckets == 0) return CVB_OK;
+  allreduce_wait_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(c, n_buckets, epoch);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}

@@ -497,24 +497,32 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int tx = threadIdx.x & 31;
   const long long split_stride = 1LL * taps * cin_pad * cout_pad;
   const int elems = taps * bci;  // (tap, i) pairs, each a 32-wide co row
-  for (int e = threadIdx.x >> 5; e < elems; e += 8) {
+  // 16-byte loads: a thread owns 4 consecutive co of one (tap, ci) row; a warp covers 4 rows x 128 bytes per load, the
+  // block 32 rows per iteration, up to four parts of a row in flight
+  const int q = tx & 7, rsub = tx >> 3;
+  for (int e = (threadIdx.x >> 5) * 4 + rsub; e < elems; e += 32) {
     const int tap = e / bci, i = e - tap * bci;
-    const int ci = ci0 + i, co = co0 + tx;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int ci = ci0 + i, co = co0 + q * 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     if (ci < cin_pad && ci < x_c && co < cout_pad) {
       const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co0 / BN;
       const int parts = item_parts(p, item);
-      const float* src = ws + (1LL * tap * cin_pad + ci) * cout_pad + co;
+      const float4* src = reinterpret_cast<const float4*>(ws + (1LL * tap * cin_pad + ci) * cout_pad + co);
+      const long long ss = split_stride >> 2;
+      auto add = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
       int s = 0;
-      for (; s + 3 < parts; s += 4) {  // four independent loads in flight
-        a0 += __ldcs(src + s * split_stride);
-        a1 += __ldcs(src + (s + 1) * split_stride);
-        a2 += __ldcs(src + (s + 2) * split_stride);
-        a3 += __ldcs(src + (s + 3) * split_stride);
+      for (; s + 3 < parts; s += 4) {
+        const float4 v0 = __ldcs(src + s * ss), v1 = __ldcs(src + (s + 1) * ss), v2 = __ldcs(src + (s + 2) * ss),
+                     v3 = __ldcs(src + (s + 3) * ss);
+        add(a0, v0); add(a1, v1); add(a2, v2); add(a3, v3);
       }
-      for (; s < parts; ++s) a0 += __ldcs(src + s * split_stride);
+      for (; s < parts; ++s) add(a0, __ldcs(src + s * ss));
     }
-    tile[(tap * bci + i) * 33 + tx] = (a0 + a1) + (a2 + a3);
+    float* t = tile + (tap * bci + i) * 33 + q * 4;
+    t[0] = (a0.x + a1.x) + (a2.x + a3.x);
+    t[1] = (a0.y + a1.y) + (a2.y + a3.y);
+    t[2] = (a0.z + a1.z) + (a2.z + a3.z);
+    t[3] = (a0.w + a1.w) + (a2.w + a3.w);
   }
   __syncthreads();
   const int row_elems = bci * taps;  // contiguous in OIHW for a fixed co

@@ -299,8 +299,12 @@ class Plan:
 
     def _begin_backward(self):
         """Flat fp32 gradient buffer of this pass; under data parallelism its ranges are all-reduced as they fill."""
-        flat = torch.zeros(self.flat_size, device=self.device)  # one memset instead of a fill per conv-bias slice
         self.reducer = self.module.__dict__.get("_cvb_reducer")
+        if self.reducer is not None and hasattr(self.reducer, "buffer"):
+            # NVLink reducer: the pass writes straight into the peer-mapped buffer the all-reduce kernel works on
+            flat = self.reducer.buffer(self.flat_size, self.device, self.param_list())
+        else:
+            flat = torch.zeros(self.flat_size, device=self.device)  # one memset instead of a fill per conv-bias slice
         if self.reducer is not None:
             self.reducer.begin(flat)
         if OVERLAP_WGRAD:
