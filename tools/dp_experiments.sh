@@ -16,11 +16,12 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run default CVB_X=0
+run nccl CVB_DP_BACKEND=nccl
+run nvlink CVB_DP_BACKEND=nvlink
 run no_exchange CVB_DP_PAYLOAD=none
-run one_bucket CVB_BUCKET_MB=100000
-run max_ctas4 NCCL_MAX_CTAS=4
-run max_ctas16 NCCL_MAX_CTAS=16
-run bf16 CVB_DP_PAYLOAD=bf16
-run bucket100 CVB_BUCKET_MB=100
-run default2 CVB_X=0
+run nccl_one_bucket CVB_DP_BACKEND=nccl CVB_BUCKET_MB=100000
+run nccl_max_ctas4 CVB_DP_BACKEND=nccl NCCL_MAX_CTAS=4
+run nvlink_ctas8 CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=8
+run nvlink_ctas96 CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=96
+run nccl_b CVB_DP_BACKEND=nccl
+run nvlink_b CVB_DP_BACKEND=nvlink
