@@ -87,27 +87,35 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
   if (v_hi > v_lo) {
     const long long n4 = (v_hi - v_lo) >> 2;
     const long long stride = 1LL * gridDim.x * kArThreads;
-    for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += 2 * stride) {
-      const long long e0 = v_lo + 4 * i, e1 = e0 + 4 * stride;
-      const bool two = i + stride < n4;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    constexpr int U = 4;  // vectors per thread and iteration: world x U peer loads (16 bytes each) in flight per thread
+    for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += U * stride) {
+      float4 a[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        on[u] = i + u * stride < n4;
+      }
 #pragma unroll
       for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {  // rank order: the same sum on every rank, every step
         if (p >= c.world) break;
-        const float4 v0 = ld_sys_f4(c.bufs[p] + e0);
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        if (two) {
-          const float4 v1 = ld_sys_f4(c.bufs[p] + e1);
-          a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!on[u]) continue;
+          const float4 v = ld_sys_f4(c.bufs[p] + v_lo + 4 * (i + u * stride));
+          a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
         }
       }
-      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
-      a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u].x *= inv; a[u].y *= inv; a[u].z *= inv; a[u].w *= inv;
+      }
 #pragma unroll
       for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {
         if (p >= c.world) break;
-        st_sys_f4(c.bufs[p] + e0, a0);
-        if (two) st_sys_f4(c.bufs[p] + e1, a1);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (on[u]) st_sys_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), a[u]);
       }
     }
   }
