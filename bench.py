@@ -259,6 +259,22 @@ def run_b200(args):
     dev_x = [x.to(dev) for x in host_x]
     dev_t = [t.to(dev) for t in host_t]
 
+    # HOST batches as cv2 / the dataset yield them (dataset/camvid.py:161-173): uint8 HWC images + uint8 masks, pageable
+    from camvid_b200 import data
+    host_u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8) for _ in range(nbuf)]
+    host_m8 = [t.to(torch.uint8) for t in host_t]
+
+    class Loader:
+        def __init__(self, k):
+            self.k = k
+
+        def __len__(self):
+            return self.k
+
+        def __iter__(self):
+            for i in range(self.k):
+                yield host_u8[i % nbuf], host_m8[i % nbuf]
+
     def step(x, t):
         opt.zero_grad(set_to_none=True)
         loss = loss_fn(net(x), t)
@@ -279,7 +295,7 @@ def run_b200(args):
         return tns.item()
 
     if args.mode == "eval":
-        run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, world, rank, dev)
+        run_eval(args, net, dev_x, dev_t, Loader, barrier, max_over_ranks, world, rank, dev)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -337,21 +353,6 @@ def run_b200(args):
     # ToTensor + Normalize on the device (cvb_input_stage_u8) -> fp32 NCHW images + uint8 masks for net / loss. The
     # loss of step i is read on the host after step i+1 has been enqueued (one device->host read per step without
     # draining the queue), like a training script that prints the previous iteration's loss.
-    from camvid_b200 import data
-    host_u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8) for _ in range(nbuf)]
-    host_m8 = [t.to(torch.uint8) for t in host_t]
-
-    class Loader:
-        def __init__(self, k):
-            self.k = k
-
-        def __len__(self):
-            return self.k
-
-        def __iter__(self):
-            for i in range(self.k):
-                yield host_u8[i % nbuf], host_m8[i % nbuf]
-
     def e2e_loop(k):
         pf = data.DevicePrefetcher(Loader(k), dev, mask_dtype=torch.uint8)
         pending = None
@@ -509,11 +510,11 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, world, rank, dev):
+def run_eval(args, net, dev_x, dev_t, Loader, barrier, max_over_ranks, world, rank, dev):
     """eval.py:50-72 / train.py:180-197 on the device: forward with BatchNorm folded into the conv epilogues, fused
     argmax + confusion matrix, mIoU from the (all-reduced) matrix."""
     import torch
-    from camvid_b200 import ops, parallel
+    from camvid_b200 import data, ops, parallel
     from camvid_b200.legacy.metrics import Metrics
     net.eval()
     B, nbuf = args.batch, len(dev_x)
@@ -537,13 +538,19 @@ def run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, w
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.LAUNCHES - l0) // args.steps
+    pf = data.DevicePrefetcher(Loader(3), dev, mask_dtype=torch.uint8)
+    for x, m in pf:  # warm the ring
+        estep(x, m)
+    barrier()
+    cm.zero_()
     e0.record()
     w0 = time.perf_counter()
-    for i in range(args.steps):
-        estep(host_x[i % nbuf].to(dev, non_blocking=True), host_t[i % nbuf].to(dev, non_blocking=True))
+    pf = data.DevicePrefetcher(Loader(args.steps), dev, mask_dtype=torch.uint8)
+    for x, m in pf:  # uint8 HWC images + uint8 masks from pageable host memory, ToTensor + Normalize on the device
+        estep(x, m)
     parallel.all_reduce_confusion(cm)
     m = Metrics(12, 11)
-    m._confusion_matrix += cm.cpu().numpy() / 2  # both timed loops counted the same batches
+    m._confusion_matrix += cm.cpu().numpy()  # the batches of the end-to-end loop, all ranks
     miou = float(m.iou())
     e1.record()
     barrier()
@@ -557,7 +564,7 @@ def run_eval(args, net, dev_x, dev_t, host_x, host_t, barrier, max_over_ranks, w
                f"{args.model} eval step (forward with running statistics + argmax + confusion matrix), per-GPU batch "
                f"{B}x3x{args.height}x{args.width}")),
            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": world * (host_x[0].numel() * 4 + host_t[0].numel() * 8),
+                   "h2d_bytes_per_step": world * pf.h2d_bytes // args.steps,
                    "d2h_bytes_per_step": 12 * 12 * 8 / args.steps, "ms_per_step": e2e_ms / args.steps},
            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "miou_random_init": miou}
     print(json.dumps(out), flush=True)

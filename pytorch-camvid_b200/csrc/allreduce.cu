@@ -30,21 +30,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// peer data: relaxed system-scope accesses (never served from a non-coherent cache)
-__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys_f4(float* p, const float4& v) {
-  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float ld_sys_f1(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys_f1(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// Peer DATA moves with ordinary L2-level accesses (ld.global.cg / st.global.cg: never served from this SM's L1, which is
+// not coherent with a peer's writes); the ordering comes from the flags: release / acquire at system scope around them,
+// plus a system-scope fence between the last data store and the "arrived" flag. (System-scope relaxed accesses for the
+// data itself -- the first version -- ran at ~45 GB/s: 3 ms for the 138 MB of UNet gradients on 2 GPUs.)
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) { __stcg(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float ld_peer_f1(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_peer_f1(float* p, float v) { __stcg(p, v); }
 
 struct CommDev {
   float* bufs[CVB_COMM_MAX_WORLD];
@@ -102,7 +95,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (!on[u]) continue;
-          const float4 v = ld_sys_f4(c.bufs[p] + v_lo + 4 * (i + u * stride));
+          const float4 v = ld_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride));
           a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
         }
       }
@@ -115,7 +108,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
         if (p >= c.world) break;
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (on[u]) st_sys_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), a[u]);
+          if (on[u]) st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), a[u]);
       }
     }
   }
@@ -123,9 +116,9 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
     for (long long e = lo + threadIdx.x; e < hi; e += kArThreads) {
       if (e >= v_lo && e < v_hi) continue;
       float a = 0.f;
-      for (int p = 0; p < c.world; ++p) a += ld_sys_f1(c.bufs[p] + e);
+      for (int p = 0; p < c.world; ++p) a += ld_peer_f1(c.bufs[p] + e);
       a *= inv;
-      for (int p = 0; p < c.world; ++p) st_sys_f1(c.bufs[p] + e, a);
+      for (int p = 0; p < c.world; ++p) st_peer_f1(c.bufs[p] + e, a);
     }
   }
   // (4) slice r has arrived everywhere
