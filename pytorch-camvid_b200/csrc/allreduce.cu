@@ -30,14 +30,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Peer DATA moves with ordinary L2-level accesses (ld.global.cg / st.global.cg: never served from this SM's L1, which is
-// not coherent with a peer's writes); the ordering comes from the flags: release / acquire at system scope around them,
-// plus a system-scope fence between the last data store and the "arrived" flag. (System-scope relaxed accesses for the
-// data itself -- the first version -- ran at ~45 GB/s: 3 ms for the 138 MB of UNet gradients on 2 GPUs.)
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) { __stcg(reinterpret_cast<float4*>(p), v); }
-__device__ __forceinline__ float ld_peer_f1(const float* p) { return __ldcg(p); }
-__device__ __forceinline__ void st_peer_f1(float* p, float v) { __stcg(p, v); }
+// Peer DATA moves with ordinary (weak) 16-byte loads and stores, like any elementwise kernel: measured 660-760 GB/s
+// per direction through these mappings on a 2 x B200 NV18 box. Ordering comes from the flags alone: st.release.sys /
+// ld.acquire.sys around them (the acquire also invalidates this SM's L1: CCTL.IVALL in the SASS) and a system-scope fence
+// between the last data store and the "arrived" flag. Strong accesses for the data are a trap: ld/st.relaxed.sys AND
+// __ldcg/__stcg (LDG/STG.STRONG.GPU) both ran at ~43 GB/s on peer memory -- 3.4 ms for the 138 MB of UNet gradients.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float ld_peer_f1(const float* p) { return *p; }
+__device__ __forceinline__ void st_peer_f1(float* p, float v) { *p = v; }
 
 struct CommDev {
   float* bufs[CVB_COMM_MAX_WORLD];
@@ -59,6 +60,7 @@ __device__ __forceinline__ long long slice_bound(long long offset, long long cou
   return a < offset + count ? a : offset + count;
 }
 
+template <int WORLD>  // compile-time rank count: WORLD x U independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, long long offset, long long count,
                                                                      int bucket, uint32_t epoch) {
   uint32_t* my_flags = c.flags[c.rank];
@@ -80,36 +82,32 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
   if (v_hi > v_lo) {
     const long long n4 = (v_hi - v_lo) >> 2;
     const long long stride = 1LL * gridDim.x * kArThreads;
-    constexpr int U = 4;  // vectors per thread and iteration: world x U peer loads (16 bytes each) in flight per thread
+    constexpr int U = WORLD <= 2 ? 4 : (WORLD <= 4 ? 2 : 1);  // vectors per thread and iteration
     for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += U * stride) {
-      float4 a[U];
+      float4 v[WORLD][U];
       bool on[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        on[u] = i + u * stride < n4;
-      }
+      for (int u = 0; u < U; ++u) on[u] = i + u * stride < n4;
 #pragma unroll
-      for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {  // rank order: the same sum on every rank, every step
-        if (p >= c.world) break;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!on[u]) continue;
-          const float4 v = ld_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride));
-          a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        a[u].x *= inv; a[u].y *= inv; a[u].z *= inv; a[u].w *= inv;
-      }
-#pragma unroll
-      for (int p = 0; p < CVB_COMM_MAX_WORLD; ++p) {
-        if (p >= c.world) break;
+      for (int p = 0; p < WORLD; ++p)  // every load first ...
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (on[u]) st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), a[u]);
+          v[p][u] = on[u] ? ld_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // ... then the sums in rank order: the same bits on every rank, every step
+        float4 a = v[0][u];
+#pragma unroll
+        for (int p = 1; p < WORLD; ++p) {
+          a.x += v[p][u].x; a.y += v[p][u].y; a.z += v[p][u].z; a.w += v[p][u].w;
+        }
+        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+        v[0][u] = a;
       }
+#pragma unroll
+      for (int p = 0; p < WORLD; ++p)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (on[u]) st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), v[0][u]);
     }
   }
   if (blockIdx.x == 0) {
@@ -178,7 +176,12 @@ extern "C" int cvb_allreduce_mean_f32(const cvb_comm* comm, int64_t offset, int6
               "allreduce: bucket %d (max %d) / epoch %u", bucket, CVB_COMM_MAX_BUCKETS, epoch);
   if (ctas < 1) ctas = 1;
   if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
-  allreduce_mean_kernel<<<ctas, kArThreads, 0, static_cast<cudaStream_t>(stream)>>>(c, offset, count, bucket, epoch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (c.world) {
+#define CVB_AR_CASE(W) case W: allreduce_mean_kernel<W><<<ctas, kArThreads, 0, st>>>(c, offset, count, bucket, epoch); break;
+    CVB_AR_CASE(1) CVB_AR_CASE(2) CVB_AR_CASE(3) CVB_AR_CASE(4) CVB_AR_CASE(5) CVB_AR_CASE(6) CVB_AR_CASE(7) CVB_AR_CASE(8)
+#undef CVB_AR_CASE
+  }
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
