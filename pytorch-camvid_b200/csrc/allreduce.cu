@@ -62,7 +62,7 @@ __device__ __forceinline__ long long slice_bound(long long offset, long long cou
 
 template <int WORLD>  // compile-time rank count: WORLD x U independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, long long offset, long long count,
-                                                                     int bucket, uint32_t epoch) {
+                                                                     int bucket, uint32_t epoch, int dbg) {
   uint32_t* my_flags = c.flags[c.rank];
   // (1) my bucket is final: every kernel that wrote it precedes this one in stream order
   if (blockIdx.x == 0 && threadIdx.x < c.world) {
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
       for (int p = 0; p < WORLD; ++p)  // every load first ...
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          v[p][u] = on[u] ? ld_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[p][u] = on[u] ? ld_peer_f4(c.bufs[((dbg & 1) && p != c.rank) ? c.rank : p] + v_lo + 4 * (i + u * stride))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < U; ++u) {  // ... then the sums in rank order: the same bits on every rank, every step
         float4 a = v[0][u];
@@ -107,12 +108,15 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
       for (int p = 0; p < WORLD; ++p)
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (on[u]) st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), v[0][u]);
+          if (on[u] && !((dbg & 2) && p != c.rank) && !((dbg & 4) && p == c.rank))
+            st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), v[0][u]);
     }
   }
-  if (blockIdx.x == 0) {
-    for (long long e = lo + threadIdx.x; e < hi; e += kArThreads) {
-      if (e >= v_lo && e < v_hi) continue;
+  if (blockIdx.x == 0 && threadIdx.x < 8) {  // ragged head [lo, v_lo) and tail [v_hi, hi): at most 3 elements each
+    const long long head = (v_hi > v_lo ? v_lo : hi) - lo;
+    const long long e = threadIdx.x < 4 ? lo + threadIdx.x : (v_hi > v_lo ? v_hi : hi) + (threadIdx.x - 4);
+    const bool mine = threadIdx.x < 4 ? threadIdx.x < head : e < hi;
+    if (mine) {
       float a = 0.f;
       for (int p = 0; p < c.world; ++p) a += ld_peer_f1(c.bufs[p] + e);
       a *= inv;
@@ -178,7 +182,12 @@ extern "C" int cvb_allreduce_mean_f32(const cvb_comm* comm, int64_t offset, int6
   if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (c.world) {
-#define CVB_AR_CASE(W) case W: allreduce_mean_kernel<W><<<ctas, kArThreads, 0, st>>>(c, offset, count, bucket, epoch); break;
+  static int dbg = -1;  // experiment knob CVB_AR_DEBUG: 1 = no remote loads, 2 = no remote stores, 4 = no local stores
+  if (dbg < 0) {
+    const char* e = getenv("CVB_AR_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+#define CVB_AR_CASE(W) case W: allreduce_mean_kernel<W><<<ctas, kArThreads, 0, st>>>(c, offset, count, bucket, epoch, dbg); break;
     CVB_AR_CASE(1) CVB_AR_CASE(2) CVB_AR_CASE(3) CVB_AR_CASE(4) CVB_AR_CASE(5) CVB_AR_CASE(6) CVB_AR_CASE(7) CVB_AR_CASE(8)
 #undef CVB_AR_CASE
   }

@@ -19,7 +19,10 @@ rank, world = dist.get_rank(), dist.get_world_size()
 sizes = [float(a) for a in sys.argv[1:]] or [138.0, 25.0, 4.0]
 for mb in sizes:
     n = int(mb * (1 << 20)) // 4
-    for backend, ctas in (("nccl", 0), ("nvlink", 16), ("nvlink", 32), ("nvlink", 64), ("nvlink", 148), ("nvlink", 296)):
+    cfgs = (("nccl", 0), ("nvlink", 16), ("nvlink", 32), ("nvlink", 64), ("nvlink", 148), ("nvlink", 296))
+    if os.environ.get("CVB_AR_DEBUG"):
+        cfgs = (("nvlink", 148),)
+    for backend, ctas in cfgs:
         if backend == "nccl":
             red = parallel.GradReducer(bucket_mb=1e9)
             flat = torch.empty(n, device=dev)
