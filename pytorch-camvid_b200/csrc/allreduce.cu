@@ -181,12 +181,12 @@ extern "C" int cvb_allreduce_mean_f32(const cvb_comm* comm, int64_t offset, int6
   if (ctas < 1) ctas = 1;
   if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (c.world) {
   static int dbg = -1;  // experiment knob CVB_AR_DEBUG: 1 = no remote loads, 2 = no remote stores, 4 = no local stores
   if (dbg < 0) {
     const char* e = getenv("CVB_AR_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
+  switch (c.world) {
 #define CVB_AR_CASE(W) case W: allreduce_mean_kernel<W><<<ctas, kArThreads, 0, st>>>(c, offset, count, bucket, epoch, dbg); break;
     CVB_AR_CASE(1) CVB_AR_CASE(2) CVB_AR_CASE(3) CVB_AR_CASE(4) CVB_AR_CASE(5) CVB_AR_CASE(6) CVB_AR_CASE(7) CVB_AR_CASE(8)
 #undef CVB_AR_CASE
