@@ -16,13 +16,15 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run nccl_one CVB_DP_BACKEND=nccl CVB_BUCKET_MB=100000
-run nvlink_one_296 CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=296
-run nvlink_one_148 CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=148
-run nvlink_one_592 CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=592
-run nccl_one_bf16 CVB_DP_BACKEND=nccl CVB_BUCKET_MB=100000 CVB_DP_PAYLOAD=bf16
-run nccl_two CVB_DP_BACKEND=nccl CVB_BUCKET_MB=70
-run nvlink_32 CVB_DP_BACKEND=nvlink
 run no_exchange CVB_DP_PAYLOAD=none
-run nccl_one_b CVB_DP_BACKEND=nccl CVB_BUCKET_MB=100000
-run nvlink_one_296_b CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=296
+run nccl CVB_DP_BACKEND=nccl
+run nccl_one CVB_DP_BACKEND=nccl CVB_BUCKET_MB=100000
+run nvlink_32 CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=32
+run nvlink_64 CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=64
+run nvlink_16 CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=16
+run nvlink_one_148 CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=148
+run nvlink_b8_64 CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=8 CVB_ALLREDUCE_CTAS=64
+run no_exchange_b CVB_DP_PAYLOAD=none
+run nccl_b CVB_DP_BACKEND=nccl
+run nvlink_64_b CVB_DP_BACKEND=nvlink CVB_ALLREDUCE_CTAS=64
+run nvlink_one_148_b CVB_DP_BACKEND=nvlink CVB_BUCKET_MB=100000 CVB_ALLREDUCE_CTAS=148
