@@ -34,15 +34,18 @@ from . import _lib
 # one all-reduce after the backward pass, nothing overlapped); CVB_DP_PAYLOAD=bf16 halves the bytes on the wire (the
 # bucket is converted on the side stream; mean of bf16-rounded gradients); CVB_DP_PAYLOAD=none skips the exchange
 # entirely (replicas drift apart: only for timing the compute without any communication).
-_BUCKET_MB = float(os.environ.get("CVB_BUCKET_MB", "25"))
+_BUCKET_MB = float(os.environ["CVB_BUCKET_MB"]) if "CVB_BUCKET_MB" in os.environ else None  # None: per-transport default
 _PAYLOAD = os.environ.get("CVB_DP_PAYLOAD", "fp32")
 
 
 class GradReducer:
     """Bucketed mean all-reduce over a flat gradient buffer whose ranges become ready front to back."""
 
+    DEFAULT_BUCKET_MB = 25.0
+
     def __init__(self, process_group=None, bucket_mb=None):
-        bucket_mb = _BUCKET_MB if bucket_mb is None else bucket_mb
+        if bucket_mb is None:
+            bucket_mb = _BUCKET_MB if _BUCKET_MB is not None else self.DEFAULT_BUCKET_MB
         if not dist.is_initialized():
             raise RuntimeError("camvid_b200.parallel: torch.distributed is not initialised")
         self.group = process_group
@@ -113,7 +116,10 @@ class PeerReducer(GradReducer):
     """The same bucket stream, exchanged by the library's own NVLink kernel on a symmetric (peer-mapped) gradient
     buffer that this reducer owns. `buffer()` hands the plan the flat buffer of a backward pass."""
 
+    # measured (tools/dp_ab.py, interleaved in one process, UNet 16 x 3 x 360 x 480 per GPU): small buckets on few CTAs
+    # disturb the backward pass least -- see DESIGN.md section 6
     CTAS = int(os.environ.get("CVB_ALLREDUCE_CTAS", "32"))
+    DEFAULT_BUCKET_MB = 8.0
 
     def __init__(self, process_group=None, bucket_mb=None):
         super().__init__(process_group, bucket_mb)

@@ -51,8 +51,10 @@ variants = {
     "nccl_25MB": nccl(25),
     "nccl_one": nccl(1e9),
     "nvlink_25MB_32": nvlink(25, 32),
-    "nvlink_25MB_64": nvlink(25, 64),
     "nvlink_8MB_32": nvlink(8, 32),
+    "nvlink_8MB_16": nvlink(8, 16),
+    "nvlink_8MB_64": nvlink(8, 64),
+    "nvlink_4MB_32": nvlink(4, 32),
     "nvlink_one_148": nvlink(1e9, 148),
 }
 names = list(variants)
