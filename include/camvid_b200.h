@@ -294,6 +294,9 @@ CVB_API int cvb_input_stage_u8(const uint8_t* img_u8, int n, int h, int w, int c
 typedef struct {
   void* const* peer_bufs_host;   /* HOST array [world] of DEVICE pointers: rank p's gradient buffer as mapped in THIS process */
   void* const* peer_flags_host;  /* HOST array [world] of DEVICE pointers: rank p's flag pad */
+  void* multicast_buf;           /* DEVICE multicast (NVLS) address of the gradient buffer, or NULL: with it the reduction
+                                    runs inside the NVSwitch (multimem.ld_reduce / multimem.st), one load + one store per
+                                    16 bytes whatever the rank count */
   int32_t rank, world;
 } cvb_comm;
 CVB_API int cvb_comm_flag_words(void);

@@ -29,7 +29,7 @@ class ConvEpilogue(ctypes.Structure):
 class Comm(ctypes.Structure):
     """cvb_comm: peer pointers of the symmetric gradient buffer / flag pad."""
     _fields_ = [("peer_bufs_host", ctypes.POINTER(ctypes.c_void_p)), ("peer_flags_host", ctypes.POINTER(ctypes.c_void_p)),
-                ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+                ("multicast_buf", ctypes.c_void_p), ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
 
 
 _P = ctypes.c_void_p

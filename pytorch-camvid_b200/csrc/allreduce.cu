@@ -43,8 +43,22 @@ __device__ __forceinline__ void st_peer_f1(float* p, float v) { *p = v; }
 struct CommDev {
   float* bufs[CVB_COMM_MAX_WORLD];
   uint32_t* flags[CVB_COMM_MAX_WORLD];
+  float* mc;  // multicast (NVLS) address of the gradient buffer, or NULL
   int rank, world;
 };
+
+// NVLink SHARP: one load returns the SUM over every rank's copy (reduced inside the NVSwitch), one store writes every
+// rank's copy. fp32 accumulation; every element is reduced once, by its slice's owner, and broadcast: identical bits on
+// all ranks.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // flag pad layout (uint32): [0, MAXB*MAXW) = "ready" [bucket][rank]; [MAXB*MAXW, 2*MAXB*MAXW) = "arrived" [bucket][rank];
 // the last word = CTA ticket of the local kernel
@@ -82,6 +96,22 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
   if (v_hi > v_lo) {
     const long long n4 = (v_hi - v_lo) >> 2;
     const long long stride = 1LL * gridDim.x * kArThreads;
+    if (c.mc != nullptr) {
+      // NVLS path: 1 load + 1 store per 16 bytes whatever the rank count (instead of WORLD + WORLD)
+      constexpr int UM = 4;
+      for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += UM * stride) {
+        float4 v[UM];
+#pragma unroll
+        for (int u = 0; u < UM; ++u)
+          if (i + u * stride < n4) v[u] = multimem_ld_reduce_f4(c.mc + v_lo + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < UM; ++u)
+          if (i + u * stride < n4) {
+            v[u].x *= inv; v[u].y *= inv; v[u].z *= inv; v[u].w *= inv;
+            multimem_st_f4(c.mc + v_lo + 4 * (i + u * stride), v[u]);
+          }
+      }
+    } else {
     constexpr int U = WORLD <= 2 ? 4 : (WORLD <= 4 ? 2 : 1);  // vectors per thread and iteration
     for (long long i = 1LL * blockIdx.x * kArThreads + threadIdx.x; i < n4; i += U * stride) {
       float4 v[WORLD][U];
@@ -110,6 +140,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(CommDev c, l
         for (int u = 0; u < U; ++u)
           if (on[u] && !((dbg & 2) && p != c.rank) && !((dbg & 4) && p == c.rank))
             st_peer_f4(c.bufs[p] + v_lo + 4 * (i + u * stride), v[0][u]);
+    }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 8) {  // ragged head [lo, v_lo) and tail [v_hi, hi): at most 3 elements each
@@ -159,6 +190,8 @@ static int load_comm(const cvb_comm* comm, CommDev* c) {
       CVB_REQUIRE((reinterpret_cast<uintptr_t>(c->bufs[p]) & 15) == 0, CVB_ERR_INVALID_ARG, "allreduce: peer buffer not 16-byte aligned");
     }
   }
+  c->mc = static_cast<float*>(comm->multicast_buf);
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(c->mc) & 15) == 0, CVB_ERR_INVALID_ARG, "allreduce: multicast address not 16-byte aligned");
   c->rank = comm->rank;
   c->world = comm->world;
   return CVB_OK;

@@ -120,6 +120,9 @@ class PeerReducer(GradReducer):
     # disturb the backward pass least -- see DESIGN.md section 6
     CTAS = int(os.environ.get("CVB_ALLREDUCE_CTAS", "32"))
     DEFAULT_BUCKET_MB = 8.0
+    # CVB_NVLS=1: reduce inside the NVSwitch through the buffer's multicast address (multimem.ld_reduce / multimem.st)
+    # where torch's symmetric memory provides one; 0 (default) = peer loads / stores
+    NVLS = os.environ.get("CVB_NVLS", "0") != "0"
 
     def __init__(self, process_group=None, bucket_mb=None):
         super().__init__(process_group, bucket_mb)
@@ -146,8 +149,11 @@ class PeerReducer(GradReducer):
         rank = dist.get_rank(group)
         self._bufs = (ctypes.c_void_p * self.world)(*[int(p) for p in h_buf.buffer_ptrs])
         self._flags = (ctypes.c_void_p * self.world)(*[int(p) for p in h_flag.buffer_ptrs])
+        mc = int(getattr(h_buf, "multicast_ptr", 0) or 0) if self.NVLS else 0
+        self.multicast = bool(mc)
         self.comm = _lib.Comm(ctypes.cast(self._bufs, ctypes.POINTER(ctypes.c_void_p)),
-                              ctypes.cast(self._flags, ctypes.POINTER(ctypes.c_void_p)), rank, self.world)
+                              ctypes.cast(self._flags, ctypes.POINTER(ctypes.c_void_p)), ctypes.c_void_p(mc or None), rank,
+                              self.world)
         self._handles = (h_buf, h_flag)
         self.size = size
 

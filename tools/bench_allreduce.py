@@ -19,7 +19,8 @@ rank, world = dist.get_rank(), dist.get_world_size()
 sizes = [float(a) for a in sys.argv[1:]] or [138.0, 25.0, 4.0]
 for mb in sizes:
     n = int(mb * (1 << 20)) // 4
-    cfgs = (("nccl", 0), ("nvlink", 16), ("nvlink", 32), ("nvlink", 64), ("nvlink", 148), ("nvlink", 296))
+    cfgs = (("nccl", 0), ("nvlink", 16), ("nvlink", 32), ("nvlink", 64), ("nvlink", 148), ("nvls", 8), ("nvls", 16), ("nvls", 32),
+            ("nvls", 64), ("nvls", 148))
     if os.environ.get("CVB_AR_DEBUG"):
         cfgs = (("nvlink", 148),)
     for backend, ctas in cfgs:
@@ -29,6 +30,7 @@ for mb in sizes:
         else:
             red = parallel.PeerReducer(bucket_mb=1e9)
             red.CTAS = ctas
+            red.NVLS = backend == "nvls"
             flat = red.buffer(n, dev)
         torch.manual_seed(rank)
         src = torch.randn(n, device=dev)
@@ -47,11 +49,11 @@ for mb in sizes:
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        err = (flat - ref).abs().max().item()
+        err = ((flat - ref).abs().max() / ref.abs().max()).item()
         t = sorted(ts[2:])[len(ts[2:]) // 2]
         tm = torch.tensor([t], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"{mb:7.1f} MB  {backend:6s} ctas {ctas:4d}  {tm.item() * 1e3:8.1f} us  algbw {mb * 1.048576 / tm.item():7.1f} GB/s  max err vs NCCL {err:.2e}",
+            print(f"{mb:7.1f} MB  {backend:6s} ctas {ctas:4d}  {tm.item() * 1e3:8.1f} us  algbw {mb * 1.048576 / tm.item():7.1f} GB/s  max err vs NCCL (rel. to max) {err:.2e}",
                   flush=True)
 dist.destroy_process_group()

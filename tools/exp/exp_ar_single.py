@@ -18,7 +18,7 @@ ref = flat.clone()
 flags = torch.zeros(lib.cvb_comm_flag_words(), dtype=torch.int32, device=dev)
 bufs = (ctypes.c_void_p * 1)(flat.data_ptr())
 fl = (ctypes.c_void_p * 1)(flags.data_ptr())
-comm = _lib.Comm(ctypes.cast(bufs, ctypes.POINTER(ctypes.c_void_p)), ctypes.cast(fl, ctypes.POINTER(ctypes.c_void_p)), 0, 1)
+comm = _lib.Comm(ctypes.cast(bufs, ctypes.POINTER(ctypes.c_void_p)), ctypes.cast(fl, ctypes.POINTER(ctypes.c_void_p)), None, 0, 1)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 epoch = 0
 for ctas in (16, 148, 592):
@@ -43,7 +43,7 @@ for off, cnt in ((1, 1003), (3, 5), (2, 4097), (0, 7)):
     x = torch.randn(8192, device=dev)
     keep = x.clone()
     b2 = (ctypes.c_void_p * 1)(x.data_ptr())
-    c2 = _lib.Comm(ctypes.cast(b2, ctypes.POINTER(ctypes.c_void_p)), ctypes.cast(fl, ctypes.POINTER(ctypes.c_void_p)), 0, 1)
+    c2 = _lib.Comm(ctypes.cast(b2, ctypes.POINTER(ctypes.c_void_p)), ctypes.cast(fl, ctypes.POINTER(ctypes.c_void_p)), None, 0, 1)
     epoch += 1
     assert lib.cvb_allreduce_mean_f32(ctypes.byref(c2), off, cnt, 0, epoch, 4, st) == 0
     torch.cuda.synchronize()
