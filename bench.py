@@ -353,11 +353,27 @@ def run_b200(args):
     # ToTensor + Normalize on the device (cvb_input_stage_u8) -> fp32 NCHW images + uint8 masks for net / loss. The
     # loss of step i is read on the host after step i+1 has been enqueued (one device->host read per step without
     # draining the queue), like a training script that prints the previous iteration's loss.
+    # One GPU: the step itself is the library's CUDA-graph step (GraphedTrainStep: same kernels, same bits, 0.3 ms of host
+    # time per step instead of 15), so that the host has room for the input pipeline; data parallel runs stay eager.
+    e2e_step, e2e_mode = step, "eager step"
+    if world == 1 and args.optimizer == "b200":
+        try:
+            from camvid_b200.graph import GraphedTrainStep
+            if graph_info is None:
+                gopt = AdamW(net.parameters(), lr=5e-4, weight_decay=0, capturable=True)
+            with torch.no_grad():
+                x0 = torch.empty(B, 3, H, W, device=dev).normal_()
+                m0 = host_m8[0].to(dev)
+            gstep8 = GraphedTrainStep(net, loss_fn, gopt, x0, m0, warmup=1)
+            e2e_step, e2e_mode = gstep8, "CUDA-graph step (camvid_b200.graph.GraphedTrainStep)"
+        except Exception as exc:  # never lose the bench line over the optional path
+            print(f"note: graphed e2e step unavailable ({type(exc).__name__}: {exc}); using the eager step", file=sys.stderr)
+
     def e2e_loop(k):
         pf = data.DevicePrefetcher(Loader(k), dev, mask_dtype=torch.uint8)
         pending = None
         for x, m in pf:
-            loss_i = step(x, m)
+            loss_i = e2e_step(x, m)
             host_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
             host_loss.copy_(loss_i.detach(), non_blocking=True)
             done = torch.cuda.Event()
@@ -382,7 +398,8 @@ def run_b200(args):
            "h2d_bytes_per_step": world * h2d // args.steps, "d2h_bytes_per_step": 4 * world,
            "ms_per_step": e2e_ms / args.steps,
            "how": "camvid_b200.data.DevicePrefetcher: uint8 HWC images + uint8 masks from pageable host memory, pinned "
-                  "ring, side-stream copy, ToTensor + Normalize on the device; loss read back with a one-step lag"}
+                  "ring, side-stream copy, ToTensor + Normalize on the device; " + e2e_mode + "; loss read back with a "
+                  "one-step lag"}
 
     # ---- data-parallel sanity (N > 1): the bucketed NCCL reducer against a plain all-reduce of rank-local gradients
     dp_check = None
@@ -404,7 +421,8 @@ def run_b200(args):
         pmax, pmin = pf_.clone(), pf_.clone()
         dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
-        dp_check = {"grad_rel_err": ((g_dp - g_ref).norm() / g_ref.norm()).item(),
+        dp_check = {"transport": type(reducer).__name__ + (" (NVLS)" if getattr(reducer, "multicast", False) else ""),
+                    "grad_rel_err": ((g_dp - g_ref).norm() / g_ref.norm()).item(),
                     "grad_max_abs_err": (g_dp - g_ref).abs().max().item(),
                     "mean_grad_norm": g_ref.norm().item(), "rank0_local_grad_norm": g_local_norm,
                     "param_spread_over_ranks_max_abs": (pmax - pmin).abs().max().item(),

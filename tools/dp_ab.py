@@ -40,22 +40,23 @@ def nccl(bucket_mb):
     return parallel.GradReducer(bucket_mb=bucket_mb)
 
 
-def nvlink(bucket_mb, ctas):
+def nvlink(bucket_mb, ctas, nvls=False):
     r = parallel.PeerReducer(bucket_mb=bucket_mb)
     r.CTAS = ctas
+    r.NVLS = nvls
     return r
 
 
 variants = {
     "none": None,
     "nccl_25MB": nccl(25),
-    "nccl_one": nccl(1e9),
     "nvlink_25MB_32": nvlink(25, 32),
     "nvlink_8MB_32": nvlink(8, 32),
-    "nvlink_8MB_16": nvlink(8, 16),
     "nvlink_8MB_64": nvlink(8, 64),
-    "nvlink_4MB_32": nvlink(4, 32),
-    "nvlink_one_148": nvlink(1e9, 148),
+    "nvls_8MB_16": nvlink(8, 16, True),
+    "nvls_8MB_32": nvlink(8, 32, True),
+    "nvls_25MB_16": nvlink(25, 16, True),
+    "nvls_4MB_16": nvlink(4, 16, True),
 }
 names = list(variants)
 
