@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 3
+#define CVB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CVB_API __attribute__((visibility("default")))
@@ -182,6 +182,18 @@ CVB_API int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scale, 
 CVB_API int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
                         const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
                         void* stream);
+/* The network's LAST block fused with the module boundary (ABI 4; cross-layer fusion). Its activation is the fp32 NCHW
+ * logits tensor the module returns (models/unet.py:156, models/segnet.py:119): dst[n,c,h,w] = float(bf16(relu(y*scale +
+ * shift))) for c < c_dst -- cvb_bn_relu_apply + cvb_nhwc_bf16_to_nchw_f32 in one pass, bit-identical to the pair; the bf16
+ * activation is never written. y.c must be 8 or 16 (the narrow class tensor), else CVB_ERR_UNSUPPORTED. */
+CVB_API int cvb_bn_relu_apply_nchw_f32(cvb_view y, const float* scale, const float* shift, float* dst, int c_dst,
+                               void* stream);
+/* ... and the entry of its backward pass (train.py:131, the gradient autograd hands to the module): src = dlogits fp32
+ * NCHW [n,c_src,h,w] -> da = bf16 NHWC view (channels >= c_src zero) AND, in the same pass, partials fp32 [rows][2][y.c] of
+ * (sum g, sum g*y), g = da * [y*scale+shift > 0] -- cvb_nchw_f32_to_nhwc_bf16 + cvb_bn_relu_bwd_reduce. Grid = rows
+ * blocks; y.c must be 8 or 16. */
+CVB_API int cvb_nchw_f32_to_nhwc_bf16_bn_reduce(const float* src, int c_src, cvb_view da, cvb_view y, const float* scale,
+                                        const float* shift, float* partials, int rows, void* stream);
 /* Backward pass 2: dy = (da*[a>0])*coef0 + y*coef1 + coef2  (bf16 view). */
 CVB_API int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale, const float* shift, const float* coef,
                           cvb_view dy, void* stream);

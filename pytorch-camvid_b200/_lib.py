@@ -62,6 +62,8 @@ SIGNATURES = {
     "cvb_bn_finalize": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     "cvb_bn_relu_apply": (_I, [View, _P, _P, View, _P]),
     "cvb_bn_relu_bwd_reduce": (_I, [View, View, _P, _P, _P, _I, _P]),
+    "cvb_bn_relu_apply_nchw_f32": (_I, [View, _P, _P, _P, _I, _P]),
+    "cvb_nchw_f32_to_nhwc_bf16_bn_reduce": (_I, [_P, _I, View, View, _P, _P, _P, _I, _P]),
     "cvb_bn_bwd_finalize": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     "cvb_bn_relu_bwd_apply": (_I, [View, View, _P, _P, _P, View, _P]),
     "cvb_maxpool2x2_fwd": (_I, [View, View, _P, _P]),
@@ -86,7 +88,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 3  # CVB_ABI_VERSION of include/camvid_b200.h this binding was written against
+ABI_VERSION = 4  # CVB_ABI_VERSION of include/camvid_b200.h this binding was written against
 
 
 def build(verbose=False):

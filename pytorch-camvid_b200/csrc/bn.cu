@@ -305,6 +305,121 @@ __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, Vi
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The network's last block, fused with the module boundary (cross-layer fusion): its
+// activation IS the fp32 NCHW logits tensor the module returns (models/unet.py:156, models/segnet.py:119), and the
+// gradient that enters its backward pass IS the fp32 NCHW dlogits of the loss.
+//   forward : logits[n,c,h,w] = float(bf16(relu(y*scale+shift)))  -- cvb_bn_relu_apply + cvb_nhwc_bf16_to_nchw_f32 in one
+//             pass; the bf16 activation is never materialised (nothing reads it: the backward mask comes from y)
+//   backward: da = bf16(dlogits) as NHWC + (sum g, sum g*y)       -- cvb_nchw_f32_to_nhwc_bf16 + cvb_bn_relu_bwd_reduce
+// Thread = one pixel (consecutive threads = consecutive pixels: every plane access of a warp is one 128-byte line, the
+// NHWC side is 32 B x CV per thread, contiguous across the warp). CV = 8-channel vectors of the narrow class tensor.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CV>
+__global__ void __launch_bounds__(kThreads) bn_relu_apply_nchw_kernel(View y, const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift,
+                                                                       float* __restrict__ dst, int c_dst) {
+  const unsigned hw = static_cast<unsigned>(y.h) * y.w;
+  const unsigned total = static_cast<unsigned>(y.n) * hw;
+  float sc[CV][8], sh[CV][8];
+#pragma unroll
+  for (int v = 0; v < CV; ++v) {
+    ld8f(scale + v * 8, sc[v]);
+    ld8f(shift + v * 8, sh[v]);
+  }
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned n = i / hw, p = i - n * hw;
+    const __nv_bfloat16* sp = y.p + poff(y, i);
+    uint4 u[CV];
+#pragma unroll
+    for (int v = 0; v < CV; ++v) u[v] = ldg16(sp + v * 8);
+    float* dp = dst + static_cast<long long>(n) * c_dst * hw + p;
+#pragma unroll
+    for (int v = 0; v < CV; ++v) {
+      float f[8];
+      unpack8(u[v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[v][j], sh[v][j]), 0.f);
+      unpack8(pack8(f), f);  // the value the unfused pair would have stored as bf16
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v * 8 + j < c_dst) dp[static_cast<long long>(v * 8 + j) * hw] = f[j];
+    }
+  }
+}
+
+template <int CV>
+__global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bn_reduce_kernel(const float* __restrict__ src, int c_src,
+                                                                           View da, View y,
+                                                                           const float* __restrict__ scale,
+                                                                           const float* __restrict__ shift,
+                                                                           float* __restrict__ partials) {
+  __shared__ float red[kThreads / 32][2 * CV * 8];
+  const unsigned hw = static_cast<unsigned>(y.h) * y.w;
+  const unsigned total = static_cast<unsigned>(y.n) * hw;
+  float sc[CV][8], sh[CV][8], s1[CV][8], s2[CV][8];
+#pragma unroll
+  for (int v = 0; v < CV; ++v) {
+    ld8f(scale + v * 8, sc[v]);
+    ld8f(shift + v * 8, sh[v]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[v][j] = s2[v][j] = 0.f;
+  }
+  for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const unsigned n = i / hw, p = i - n * hw;
+    const float* sp = src + static_cast<long long>(n) * c_src * hw + p;
+    uint4 uy[CV];
+    float g[CV][8];
+#pragma unroll
+    for (int v = 0; v < CV; ++v) uy[v] = ldg16(y.p + poff(y, i) + v * 8);
+#pragma unroll
+    for (int v = 0; v < CV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[v][j] = (v * 8 + j < c_src) ? __ldcs(sp + static_cast<long long>(v * 8 + j) * hw) : 0.f;
+    __nv_bfloat16* dp = da.p + poff(da, i);
+#pragma unroll
+    for (int v = 0; v < CV; ++v) {
+      const uint4 pk = pack8(g[v]);
+      stg16(dp + v * 8, pk);
+      float fy[8], fd[8];
+      unpack8(pk, fd);  // sums of the bf16 values the apply pass will read
+      unpack8(uy[v], fy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ge = fmaf(fy[j], sc[v][j], sh[v][j]) > 0.f ? fd[j] : 0.f;
+        s1[v][j] += ge;
+        s2[v][j] = fmaf(ge, fy[j], s2[v][j]);
+      }
+    }
+  }
+  // every thread holds all channels: fold the 32 lanes by shuffles, then the 8 warps through 1 KB of shared memory
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < CV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = s1[v][j], b = s2[v][j];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, m);
+        b += __shfl_xor_sync(0xffffffffu, b, m);
+      }
+      if (lane == 0) {
+        red[wq][v * 8 + j] = a;
+        red[wq][CV * 8 + v * 8 + j] = b;
+      }
+    }
+  __syncthreads();
+  if (threadIdx.x < 2 * CV * 8) {
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) acc += red[q][threadIdx.x];
+    const int which = threadIdx.x / (CV * 8), ch = threadIdx.x - which * (CV * 8);
+    partials[(1LL * blockIdx.x * 2 + which) * (CV * 8) + ch] = acc;
+  }
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -407,6 +522,52 @@ extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale
   else
     bn_relu_bwd_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bn_relu_apply_nchw_f32(cvb_view y, const float* scale, const float* shift, float* dst, int c_dst,
+                                          void* stream) {
+  int rc = check_view(y, "bn_relu_apply_nchw.y");
+  if (rc) return rc;
+  CVB_REQUIRE(scale && shift && dst, CVB_ERR_INVALID_ARG, "bn_relu_apply_nchw: null pointer");
+  CVB_REQUIRE(c_dst > 0 && c_dst <= y.c, CVB_ERR_INVALID_ARG, "bn_relu_apply_nchw: c_dst=%d does not fit the %d channels of y",
+              c_dst, y.c);
+  CVB_REQUIRE(y.c == 8 || y.c == 16, CVB_ERR_UNSUPPORTED,
+              "bn_relu_apply_nchw: the fused boundary kernel serves class tensors of 8 or 16 channels in memory (got %d); "
+              "use cvb_bn_relu_apply + cvb_nhwc_bf16_to_nchw_f32", y.c);
+  CVB_REQUIRE(1LL * y.n * y.h * y.w < (1LL << 31), CVB_ERR_UNSUPPORTED, "bn_relu_apply_nchw: view too large for 32-bit indexing");
+  const long long total = 1LL * y.n * y.h * y.w;
+  const int grid = ew_grid(total, kThreads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y.c == 16)
+    bn_relu_apply_nchw_kernel<2><<<grid, kThreads, 0, st>>>(to_dev(y), scale, shift, dst, c_dst);
+  else
+    bn_relu_apply_nchw_kernel<1><<<grid, kThreads, 0, st>>>(to_dev(y), scale, shift, dst, c_dst);
+  CVB_LAUNCH_CHECK();
+  return CVB_OK;
+}
+
+extern "C" int cvb_nchw_f32_to_nhwc_bf16_bn_reduce(const float* src, int c_src, cvb_view da, cvb_view y,
+                                                   const float* scale, const float* shift, float* partials, int rows,
+                                                   void* stream) {
+  int rc = check_view(y, "nchw_to_nhwc_bn_reduce.y");
+  if (rc) return rc;
+  rc = check_view(da, "nchw_to_nhwc_bn_reduce.da");
+  if (rc) return rc;
+  CVB_REQUIRE(same_shape(da, y), CVB_ERR_INVALID_ARG, "nchw_to_nhwc_bn_reduce: da and y shapes differ");
+  CVB_REQUIRE(src && scale && shift && partials && rows > 0, CVB_ERR_INVALID_ARG, "nchw_to_nhwc_bn_reduce: null pointer / rows");
+  CVB_REQUIRE(c_src > 0 && c_src <= y.c, CVB_ERR_INVALID_ARG, "nchw_to_nhwc_bn_reduce: c_src=%d does not fit the %d channels",
+              c_src, y.c);
+  CVB_REQUIRE(y.c == 8 || y.c == 16, CVB_ERR_UNSUPPORTED,
+              "nchw_to_nhwc_bn_reduce: the fused boundary kernel serves class tensors of 8 or 16 channels in memory (got %d); "
+              "use cvb_nchw_f32_to_nhwc_bf16 + cvb_bn_relu_bwd_reduce", y.c);
+  CVB_REQUIRE(1LL * y.n * y.h * y.w < (1LL << 31), CVB_ERR_UNSUPPORTED, "nchw_to_nhwc_bn_reduce: view too large for 32-bit indexing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y.c == 16)
+    nchw_to_nhwc_bn_reduce_kernel<2><<<rows, kThreads, 0, st>>>(src, c_src, to_dev(da), to_dev(y), scale, shift, partials);
+  else
+    nchw_to_nhwc_bn_reduce_kernel<1><<<rows, kThreads, 0, st>>>(src, c_src, to_dev(da), to_dev(y), scale, shift, partials);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -32,6 +32,10 @@ FUSE_BWD_STATS = os.environ.get("CVB_FUSE_BWD", "0") != "0"
 # MaxPool backward emits the BatchNorm+ReLU backward reduction of the block it feeds (cvb_maxpool2x2_bwd_bn_reduce): the
 # reduce pass over the largest activations of the encoder disappears (4 of 23 passes in UNet, 5 of 26 in SegNet).
 FUSE_POOL_BWD_REDUCE = os.environ.get("CVB_FUSE_POOL_BWD", "1") != "0"
+# The last block is fused with the module boundary: its BatchNorm+ReLU writes the fp32 NCHW logits directly
+# (cvb_bn_relu_apply_nchw_f32) and the fp32 NCHW gradient of the loss is converted AND reduced for its BatchNorm backward
+# in one pass (cvb_nchw_f32_to_nhwc_bf16_bn_reduce): two full-resolution HBM passes and two launches fewer per step.
+FUSE_BOUNDARY = os.environ.get("CVB_FUSE_BOUNDARY", "1") != "0"
 SERIALIZE_TENSOR_KERNELS = os.environ.get("CVB_SERIALIZE_TENSOR", "0") != "0"  # measured: see DESIGN.md knobs
 
 
@@ -99,7 +103,11 @@ class Block:
             ops.pack_weights_dgrad(self.conv.weight.detach(), self.cout_pad, self.cin_pad, out=self.wd)
             self.wd_version = key
 
-    def forward_train(self, pool_out=None, code=None):
+    def fuses_boundary(self):
+        """Whether this block, as the network's last one, can write the logits / read the loss gradient directly."""
+        return FUSE_BOUNDARY and self.ce in (8, 16)
+
+    def forward_train(self, pool_out=None, code=None, logits_out=None):
         p, bn = self.plan, self.bn
         self._pack_f()
         parts = p.parts_view(self.cout_pad)
@@ -112,7 +120,11 @@ class Block:
                         bn.bias.detach(), self.conv.bias.detach() if self.conv.bias is not None else None,
                         bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
                         v[0], v[1], v[2], v[3])
-        if pool_out is not None:
+        if logits_out is not None:
+            # the network's last block: its activation is the fp32 NCHW tensor the module returns; the bf16 copy in
+            # self.a is not written (backward takes the ReLU mask from y)
+            ops.bn_relu_apply_nchw(self.y_e, v[2], v[3], logits_out)
+        elif pool_out is not None:
             ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
         else:
             ops.bn_relu_apply(self.y_e, v[2], v[3], self.a_e)
@@ -271,6 +283,27 @@ class Plan:
             if b.taps != 9:
                 b._pack_f()
 
+    def _logits_train(self, block):
+        """Train-mode forward of the last block + the fp32 NCHW logits handed back to autograd."""
+        logits = torch.empty(self.n, self.class_num, self.h, self.w, device=self.device)
+        if block.fuses_boundary():
+            block.forward_train(logits_out=logits)
+        else:
+            block.forward_train()
+            ops.nhwc_to_nchw(self.out_a, logits)
+        return logits
+
+    def _enter_backward(self, block, dlogits):
+        """fp32 NCHW gradient of the loss -> bf16 NHWC `da` of the last block. Returns the `stats_ready` argument of that
+        block's backward: the number of partial rows when the conversion also emitted its BatchNorm backward reduction."""
+        da = self.d_out_a[..., :block.ce]
+        if block.fuses_boundary():
+            ops.nchw_to_nhwc_bn_reduce(dlogits, da, block.y_e, block.vec[2], block.vec[3], self.parts_view(block.ce),
+                                       self.reduce_rows)
+            return self.reduce_rows
+        ops.nchw_to_nhwc(dlogits, da)
+        return False
+
     def param_list(self):
         out = []
         for b in self.blocks:
@@ -418,18 +451,20 @@ class UNetPlan(Plan):
             ops.bilinear2x(d["src"], d["up"])
             for b in (d["bu"], d["b0"], d["b1"]):
                 b.forward_train() if train else b.forward_eval()
-        self.b_out.forward_train() if train else self.b_out.forward_eval()
         if train:
+            logits = self._logits_train(self.b_out)
             self._bump_batches_tracked()
+            return logits
+        self.b_out.forward_eval()
         logits = torch.empty(self.n, self.class_num, self.h, self.w, device=self.device)
         ops.nhwc_to_nchw(self.out_a, logits)
         return logits
 
     def backward(self, dlogits):
         flat = self._begin_backward()
-        ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.b_out.ce])
+        ready = self._enter_backward(self.b_out, dlogits)
         last = self.dec[-1]
-        ready = self.b_out.backward(self.d_out_a, last["dm1"], flat, consumer=last["b1"])
+        ready = self.b_out.backward(self.d_out_a, last["dm1"], flat, consumer=last["b1"], stats_ready=ready)
         self._done(self.b_out)
         for d in reversed(self.dec):
             l = d["level"]
@@ -531,22 +566,30 @@ class SegNetPlan(Plan):
                     b.forward_eval()
             if not train:
                 ops.maxpool2x2(bl[-1].a, st["pooled"], st["code"])
+        last = self.dstages[-1]["blocks"][-1]
+        logits = None
         for ds in self.dstages:
             ops.maxunpool2x2(ds["src"], ds["code"], ds["un"])
             for b in ds["blocks"]:
-                b.forward_train() if train else b.forward_eval()
+                if not train:
+                    b.forward_eval()
+                elif b is last:
+                    logits = self._logits_train(b)
+                else:
+                    b.forward_train()
         if train:
             self._bump_batches_tracked()
+            return logits
         logits = torch.empty(self.n, self.class_num, self.h, self.w, device=self.device)
         ops.nhwc_to_nchw(self.out_a, logits)
         return logits
 
     def backward(self, dlogits):
         flat = self._begin_backward()
-        ops.nchw_to_nhwc(dlogits, self.d_out_a[..., :self.dstages[-1]["blocks"][-1].ce])
+        entry = self._enter_backward(self.dstages[-1]["blocks"][-1], dlogits)
         for ds in reversed(self.dstages):
             bl = ds["blocks"]
-            ready = False
+            ready = entry if ds is self.dstages[-1] else False
             for j in range(len(bl) - 1, -1, -1):
                 ready = bl[j].backward(ds["dacts"][j], ds["dacts"][j - 1] if j > 0 else ds["dun"], flat,
                                        consumer=bl[j - 1] if j > 0 else None, stats_ready=ready)

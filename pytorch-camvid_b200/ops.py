@@ -270,6 +270,22 @@ def bn_relu_bwd_reduce(da, y, scale, shift, partials, rows):
           _ptr(shift), _ptr(partials), rows, _stream())
 
 
+def bn_relu_apply_nchw(y, scale, shift, dst):
+    """Last block + module boundary: dst fp32 [N,C,H,W] = float(bf16(relu(y*scale+shift))) from the NHWC bf16 view y."""
+    _f32(dst, "bn_relu_apply_nchw.dst")
+    _call("bn_relu_apply_nchw", 1, _nbytes(y, dst), _lib.load().cvb_bn_relu_apply_nchw_f32, view(y), _ptr(scale),
+          _ptr(shift), _ptr(dst), dst.shape[1], _stream())
+    return dst
+
+
+def nchw_to_nhwc_bn_reduce(src, da, y, scale, shift, partials, rows):
+    """Entry of the last block's backward: da = bf16 NHWC of the fp32 NCHW gradient `src` + the BatchNorm+ReLU backward
+    reduction over (da, y) in the same pass."""
+    _f32(src, "nchw_to_nhwc_bn_reduce.src")
+    _call("nchw_to_nhwc_bn_reduce", 1, _nbytes(src, da, y), _lib.load().cvb_nchw_f32_to_nhwc_bf16_bn_reduce, _ptr(src),
+          src.shape[1], view(da), view(y), _ptr(scale), _ptr(shift), _ptr(partials), rows, _stream())
+
+
 def bn_bwd_finalize(partials, rows, c, c_pad, count, gamma, mean, invstd, dgamma, dbeta, coef):
     _call("bn_bwd_finalize", 1, ("bytes", rows * 2 * c_pad * 4.0), _lib.load().cvb_bn_bwd_finalize, _ptr(partials),
           rows, c, c_pad, count, _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta), _ptr(coef),

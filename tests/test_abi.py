@@ -20,7 +20,7 @@ def _header_symbols():
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.cvb_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.cvb_abi_version() == _lib.ABI_VERSION == 4
     declared = _header_symbols()
     assert len(declared) >= 30
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout

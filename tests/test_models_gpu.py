@@ -128,7 +128,7 @@ def _oracle_steps_with_records(name, sd, x, t, ignore_index=-100):
     return out
 
 
-def _check_layer_trajectory(net, rec32, rec16, tag):
+def _check_layer_trajectory(net, rec32, rec16, tag, logits=None):
     """Whole-model check that stays non-vacuous where the end-to-end envelope is not (SegNet: bf16 storage alone puts
     the logits ~0.7 from fp32): the activation of EVERY block, read back from the plan after the step, against the
     fp32 oracle's activation of that block. The bf16 storage model's own distance from fp32 starts at 3e-3 at the first
@@ -139,7 +139,10 @@ def _check_layer_trajectory(net, rec32, rec16, tag):
     rows, worst = [], 0.0
     for b in plan.blocks:
         key = b.name + ".conv" if b.name.startswith("upsample") else b.name
-        act = b.a[..., :b.cout].float().permute(0, 3, 1, 2).cpu()
+        if b is plan.blocks[-1] and b.fuses_boundary():
+            act = logits  # the last block writes the fp32 NCHW logits directly; its bf16 activation is never materialised
+        else:
+            act = b.a[..., :b.cout].float().permute(0, 3, 1, 2).cpu()
         e_cuda, e_model = rel_err(act, rec32[key]["out"]), rel_err(rec16[key]["out"], rec32[key]["out"])
         e_pair = rel_err(act, rec16[key]["out"])
         limit = max(TOL_LOGITS, 1.5 * e_model)
@@ -227,7 +230,7 @@ def test_train_step_matches_oracle(cvb, cuda, name, n, h, w):
         _oracle_steps_with_records(name, sd, x, t)
     _check_within_bf16_envelope(net, loss, logits, o_loss, o_logits, o_grads, m_logits, m_grads)
     _check_grad_norms(net, o_grads)
-    _check_layer_trajectory(net, rec32, rec16, f"{name} {n}x{h}x{w}")
+    _check_layer_trajectory(net, rec32, rec16, f"{name} {n}x{h}x{w}", logits)
     _check_logit_statistics(logits, o_logits, m_logits, f"{name} {n}x{h}x{w}")
     after = net.state_dict()
     stat_keys = [k for k in o_after if k.endswith(("running_mean", "running_var"))]
@@ -249,7 +252,7 @@ def test_full_resolution_step(cvb, cuda, name):
         _oracle_steps_with_records(name, sd, x, t)
     _check_within_bf16_envelope(net, loss, logits, o_loss, o_logits, o_grads, m_logits, m_grads)
     _check_grad_norms(net, o_grads)
-    _check_layer_trajectory(net, rec32, rec16, f"{name} 2x360x480")
+    _check_layer_trajectory(net, rec32, rec16, f"{name} 2x360x480", logits)
     _check_logit_statistics(logits, o_logits, m_logits, f"{name} 2x360x480")
 
 

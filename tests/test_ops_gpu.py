@@ -284,6 +284,46 @@ def test_bn_relu_train(ops, cuda, n, h, w, c, creal):
     assert torch.count_nonzero(dy[..., creal:]) == 0
 
 
+@pytest.mark.parametrize("n,h,w,cmem,stride_c,creal", [(2, 36, 40, 16, 16, 12), (1, 45, 61, 16, 64, 12),
+                                                        (3, 17, 9, 8, 8, 5), (2, 360, 480, 16, 16, 12)])
+def test_last_block_fused_with_the_module_boundary_is_bit_identical(ops, cuda, n, h, w, cmem, stride_c, creal):
+    """cvb_bn_relu_apply_nchw_f32 == cvb_bn_relu_apply + cvb_nhwc_bf16_to_nchw_f32 and
+    cvb_nchw_f32_to_nhwc_bf16_bn_reduce == cvb_nchw_f32_to_nhwc_bf16 + cvb_bn_relu_bwd_reduce (same da bits, same sums
+    up to fp32 summation order), on dense and channel-strided views (the odd-height plans keep 64 channels in memory)."""
+    buf = torch.zeros(n, h, w, stride_c, dtype=torch.bfloat16, device=cuda)
+    buf[..., :creal] = to_nhwc_bf16(_rand((n, creal, h, w), cuda, 61))
+    y = buf[..., :cmem]
+    scale = torch.zeros(cmem, device=cuda)
+    shift = torch.zeros(cmem, device=cuda)
+    scale[:creal] = torch.rand(creal, device=cuda) + 0.5
+    shift[:creal] = torch.randn(creal, device=cuda) * 0.3
+    # forward
+    a = torch.empty(n, h, w, cmem, dtype=torch.bfloat16, device=cuda)
+    want = torch.empty(n, creal, h, w, device=cuda)
+    ops.bn_relu_apply(y, scale, shift, a)
+    ops.nhwc_to_nchw(a, want)
+    got = torch.full((n, creal, h, w), float("nan"), device=cuda)
+    ops.bn_relu_apply_nchw(y, scale, shift, got)
+    assert torch.equal(got, want)
+    # backward entry
+    dl = torch.randn(n, creal, h, w, device=cuda) * 1e-3  # fp32, not bf16-representable: the kernel rounds
+    rows = 4 * ops.sm_count()
+    da_want = torch.full((n, h, w, cmem), 7.0, dtype=torch.bfloat16, device=cuda)
+    ref = torch.empty(rows, 2, cmem, device=cuda)
+    ops.nchw_to_nhwc(dl, da_want)
+    ops.bn_relu_bwd_reduce(da_want, y, scale, shift, ref, rows)
+    da_buf = torch.full((n, h, w, stride_c), 7.0, dtype=torch.bfloat16, device=cuda)
+    da_got = da_buf[..., :cmem]
+    parts = torch.full((rows, 2, cmem), float("nan"), device=cuda)
+    ops.nchw_to_nhwc_bn_reduce(dl, da_got, y, scale, shift, parts, rows)
+    assert torch.equal(da_got, da_want)
+    if stride_c > cmem:
+        assert (da_buf[..., cmem:] == 7.0).all()  # nothing written outside the view
+    g, r = parts.double().sum(0), ref.double().sum(0)
+    assert torch.isfinite(g).all()
+    assert rel_err(g[0], r[0]) < 1e-5 and rel_err(g[1], r[1]) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------- pooling
 @pytest.mark.parametrize("n,h,w,c", [(2, 8, 12, 64), (1, 45, 61, 64), (3, 11, 15, 128)])
 def test_maxpool_indices_bit_exact(ops, cuda, n, h, w, c):
