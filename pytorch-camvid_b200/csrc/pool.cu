@@ -188,73 +188,94 @@ __global__ void __launch_bounds__(kThreads) pool_gather_kernel(View dout, View d
 // section 8(f) rank 1, producer side): the kernel that last writes `da` -- the gradient w.r.t. that block's activation -- also
 // emits the per-channel sums (g, g*y) with g = da * [y*scale+shift > 0] that cvb_bn_relu_bwd_reduce would otherwise
 // re-read da and y from HBM for: per element 6.75 B (y, da in/out, dout/4, code/4) instead of 6.5 + 4.
-// Built like bn_reduce_kernel, one thread = 8 channels of one PIXEL (not of a window: a window-per-thread version
-// needed 128+ registers and ran at 3.2 TB/s, slower than the two kernels it replaced): the pixel looks up its window's
-// code and pooled gradient (read by its three neighbours too: L1 / L2 hits). A thread keeps one channel group, blocks
-// stride over pixels, one partial row per block. Sums are taken from the bf16-rounded da that is stored, so the result
-// is bit-identical to the unfused pair.
+// One thread = 8 channels of one COLUMN of a row pair (the two pixels (2hp, w), (2hp+1, w) share their window's pooled
+// gradient and code: 6 loads for 2 pixels; a whole window per thread needed 128+ registers and ran slower than the two
+// kernels it replaced). A thread keeps one channel group; blocks stride over (row pair, column chunk) items, one
+// partial row per block. Sums are taken from the bf16-rounded da that is stored, so the result is bit-identical to the
+// unfused pair. The first version indexed pixels linearly (two divisions and three 64-bit stride products per pixel)
+// and was ISSUE-bound at 267 instructions per pixel vector (ncu, profiles/r02n_elementwise_full.md); here the row
+// bases are computed once per item, the item -> (image, row pair, chunk) split uses host-made reciprocals, and the
+// window codes are compared as bytes.
+struct PoolBwdGeom {
+  unsigned chunks;       // column chunks (of ppb columns) per row pair
+  unsigned hp;           // row pairs per image = ceil(h / 2)
+  unsigned items;        // n * hp * chunks
+  unsigned magic_chunks; // ceil(2^32 / chunks)      (exact quotient for every item index: checked on the host)
+  unsigned magic_hp;     // ceil(2^32 / hp)
+};
+
+__device__ __forceinline__ unsigned div_magic(unsigned x, unsigned d, unsigned magic) {
+  return d == 1 ? x : __umulhi(x, magic);
+}
+
 template <bool ACCUM>
 __global__ void __launch_bounds__(kThreads, 3) pool_bwd_bn_reduce_kernel(View dout, View y, View dx,
                                                                        const uint8_t* __restrict__ code,
                                                                        const float* __restrict__ scale,
                                                                        const float* __restrict__ shift,
-                                                                       float* __restrict__ partials) {
+                                                                       float* __restrict__ partials, PoolBwdGeom gm) {
   __shared__ float red[kThreads * 2];
   const int CV = dx.c >> 3;
   const int ppb = kThreads / CV;
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
-  const unsigned npix = 1u * dx.n * dx.h * dx.w;
   float sc[8], sh[8], s1[8], s2[8];
   ld8f(scale + cv * 8, sc);
   ld8f(shift + cv * 8, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const unsigned step = gridDim.x * ppb;
-  for (unsigned pix0 = blockIdx.x * ppb + pl; pix0 < npix; pix0 += 2 * step) {
-    // two pixels per iteration, every load issued before the arithmetic
-    uint4 uy[2], ud[2], ug[2];
-    unsigned kk[2];  // position of the pixel in its window
-    uint2 uc[2];
-    bool live[2], full[2];
-    __nv_bfloat16* dst[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const unsigned pix = pix0 + q * step;
-      live[q] = pix < npix;
-      full[q] = false;
-      uy[q] = ud[q] = ug[q] = make_uint4(0u, 0u, 0u, 0u);
-      uc[q] = make_uint2(0u, 0u);
-      if (!live[q]) continue;
-      unsigned t = pix;
-      const int w = static_cast<int>(t % dx.w);
-      t /= dx.w;
-      const int h = static_cast<int>(t % dx.h);
-      const int n = static_cast<int>(t / dx.h);
-      const int ho = h >> 1, wo = w >> 1;
-      kk[q] = static_cast<unsigned>((h & 1) * 2 + (w & 1));
-      full[q] = ho < dout.h && wo < dout.w;  // odd last row / column: no window, the gradient passes through unchanged
-      dst[q] = dx.p + voff(dx, n, h, w) + cv * 8;
-      uy[q] = ldg16(y.p + voff(y, n, h, w) + cv * 8);
-      if (ACCUM) ud[q] = *reinterpret_cast<const uint4*>(dst[q]);
-      if (full[q]) {
-        ug[q] = ldg16(dout.p + voff(dout, n, ho, wo) + cv * 8);
-        uc[q] = __ldg(reinterpret_cast<const uint2*>(code + ((1LL * n * dout.h + ho) * dout.w + wo) * dx.c + cv * 8));
-      }
+  // 32-bit element strides (one image of each view and the code tensor fit 32-bit offsets: checked on the host); only the
+  // image base is a 64-bit product
+  const unsigned ysw = static_cast<unsigned>(y.sw), ysh = static_cast<unsigned>(y.sh), ysn = static_cast<unsigned>(y.sn);
+  const unsigned xsw = static_cast<unsigned>(dx.sw), xsh = static_cast<unsigned>(dx.sh), xsn = static_cast<unsigned>(dx.sn);
+  const unsigned osw = static_cast<unsigned>(dout.sw), osh = static_cast<unsigned>(dout.sh), osn = static_cast<unsigned>(dout.sn);
+  const unsigned H = static_cast<unsigned>(dx.h), W = static_cast<unsigned>(dx.w), HO = static_cast<unsigned>(dout.h),
+                 WO = static_cast<unsigned>(dout.w), C = static_cast<unsigned>(dx.c);
+  const unsigned cvo = static_cast<unsigned>(cv) * 8u;
+  for (unsigned it = blockIdx.x; it < gm.items; it += gridDim.x) {
+    const unsigned rp = div_magic(it, gm.chunks, gm.magic_chunks);  // (image, row pair)
+    const unsigned chunk = it - rp * gm.chunks;
+    const unsigned n = div_magic(rp, gm.hp, gm.magic_hp);
+    const unsigned hp = rp - n * gm.hp;
+    const unsigned w = chunk * static_cast<unsigned>(ppb) + static_cast<unsigned>(pl);
+    if (w >= W) continue;
+    const unsigned h0 = 2u * hp, wo = w >> 1;
+    const bool two = h0 + 1u < H;                  // odd last row: a single pixel, no window
+    const bool full = two && hp < HO && wo < WO;   // odd last column: no window, the gradient passes through
+    const __nv_bfloat16* yp = y.p + static_cast<size_t>(n) * ysn + (h0 * ysh + w * ysw + cvo);
+    __nv_bfloat16* dp = dx.p + static_cast<size_t>(n) * xsn + (h0 * xsh + w * xsw + cvo);
+    uint4 uy[2], ud[2], ug = make_uint4(0u, 0u, 0u, 0u);
+    uint2 uc = make_uint2(0u, 0u);
+    uy[0] = ldg16(yp);
+    uy[1] = two ? ldg16(yp + ysh) : make_uint4(0u, 0u, 0u, 0u);
+    ud[0] = ud[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (ACCUM) {
+      ud[0] = *reinterpret_cast<const uint4*>(dp);
+      if (two) ud[1] = *reinterpret_cast<const uint4*>(dp + xsh);
     }
+    if (full) {
+      ug = ldg16(dout.p + static_cast<size_t>(n) * osn + (hp * osh + wo * osw + cvo));
+      uc = __ldg(reinterpret_cast<const uint2*>(code + (((n * HO + hp) * WO + wo) * C + cvo)));
+    }
+    float g[8];
+    unpack8(ug, g);
+    // the window position of this column's two pixels: (w & 1) in the top row, 2 + (w & 1) in the bottom row; a code
+    // byte can only equal one of them, and none when the window does not exist (ug = 0 then anyway)
+    const unsigned k0 = w & 1u, k1 = k0 + 2u;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      if (!live[q]) continue;
-      float o[8], g[8], fy[8];
-      uint32_t cd[8];
+      if (q == 1 && !two) break;
+      float o[8], fy[8];
       unpack8(ud[q], o);  // zeros unless ACCUM
-      unpack8(ug[q], g);
       unpack8(uy[q], fy);
-      unpack_code(uc[q], cd);
+      const unsigned kq = q == 0 ? k0 : k1;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (full[q] && cd[j] == kk[q]) ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const unsigned cj = ((j < 4 ? uc.x : uc.y) >> (8 * (j & 3))) & 0xffu;
+        o[j] += (full && cj == kq) ? g[j] : 0.f;
+      }
       const uint4 pk = pack8(o);
-      if (!ACCUM || full[q]) stg16(dst[q], pk);
+      if (!ACCUM || full) stg16(dp + q * xsh, pk);
       unpack8(pk, o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -264,7 +285,6 @@ __global__ void __launch_bounds__(kThreads, 3) pool_bwd_bn_reduce_kernel(View do
       }
     }
   }
-  const int C = dx.c;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {  // cross-thread combine through 2 KB (see bn_reduce_kernel: must fit beside a wgrad CTA)
     red[threadIdx.x * 2] = s1[j];
@@ -274,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 3) pool_bwd_bn_reduce_kernel(View do
       const int which = threadIdx.x / CV, ocv = threadIdx.x - which * CV;
       float acc = 0.f;
       for (int l = 0; l < ppb; ++l) acc += red[(l * CV + ocv) * 2 + which];
-      partials[(1LL * blockIdx.x * 2 + which) * C + ocv * 8 + j] = acc;
+      partials[(1LL * blockIdx.x * 2 + which) * dx.c + ocv * 8 + j] = acc;
     }
     __syncthreads();
   }
@@ -390,11 +410,26 @@ extern "C" int cvb_maxpool2x2_bwd_bn_reduce(cvb_view dout, const uint8_t* code, 
   CVB_REQUIRE(1LL * dx.n * dx.h * dx.w < (1LL << 31), CVB_ERR_UNSUPPORTED,
               "maxpool_bwd_bn_reduce: view too large for 32-bit indexing");
   CVB_REQUIRE(code, CVB_ERR_INVALID_ARG, "maxpool_bwd_bn_reduce: null index codes (cvb_bn_relu_maxpool2x2_fwd writes them)");
+  CVB_REQUIRE(1LL * dx.h * dx.sh < (1LL << 31) && 1LL * dout.h * dout.sh < (1LL << 31) && 1LL * y.h * y.sh < (1LL << 31) &&
+                  dx.sn < (1LL << 31) && dout.sn < (1LL << 31) && y.sn < (1LL << 31) &&
+                  1LL * dout.n * dout.h * dout.w * dx.c < (1LL << 32),
+              CVB_ERR_UNSUPPORTED, "maxpool_bwd_bn_reduce: one image (or the code tensor) exceeds 32-bit element offsets");
+  PoolBwdGeom gm;
+  const int ppb = kThreads / CV;
+  gm.chunks = static_cast<unsigned>((dx.w + ppb - 1) / ppb);
+  gm.hp = static_cast<unsigned>((dx.h + 1) / 2);
+  const long long items = 1LL * dx.n * gm.hp * gm.chunks;
+  gm.items = static_cast<unsigned>(items);
+  gm.magic_chunks = static_cast<unsigned>(((1ULL << 32) + gm.chunks - 1) / gm.chunks);
+  gm.magic_hp = static_cast<unsigned>(((1ULL << 32) + gm.hp - 1) / gm.hp);
+  // x / d == umulhi(x, ceil(2^32 / d)) for every x < 2^32 / d (round-up reciprocal: error x * (d - 1) / 2^32 < 1 / d... checked)
+  CVB_REQUIRE(items * gm.chunks < (1LL << 32) && items * gm.hp < (1LL << 32), CVB_ERR_UNSUPPORTED,
+              "maxpool_bwd_bn_reduce: view too large for the reciprocal index split");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (accumulate)
-    pool_bwd_bn_reduce_kernel<true><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
+    pool_bwd_bn_reduce_kernel<true><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials, gm);
   else
-    pool_bwd_bn_reduce_kernel<false><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials);
+    pool_bwd_bn_reduce_kernel<false><<<rows, kThreads, 0, st>>>(to_dev(dout), to_dev(y), to_dev(dx), code, scale, shift, partials, gm);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -124,11 +124,18 @@ __device__ __forceinline__ int gather_taps(float scale, float inv, int in, int o
 // y0 + 1 of that output row). 4-5 loads per output row instead of 16-25 per input pixel.
 // NT = tap slots along x: 4 is exact for every 2x align_corners upsampling of an input wider than 1 (each input
 // column is touched by 4 output columns, 3 at the edges -- counted on the host, which falls back to 6 slots otherwise).
+// The loop body is kept lean on purpose: ncu (profiles/r02n_elementwise_full.md) showed the previous version ISSUE-bound
+// at 227 instructions per (thread, output row) -- 64-bit address products per tap, L2 prefetches, the row bounds tested
+// inside the loop -- against ~100 of payload (4 loads, 32 conversions, 48 FMAs). Now: tap offsets are 32-bit element
+// offsets computed once per thread, the row pointer advances by one add, the first / last output row of the strip are
+// found before the loop (no continue / break inside), and since consecutive output rows map to source rows at most one
+// apart (scale < 1/2) the accumulator roll is a single `if`.
 template <int NT>
 __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, View dx, float sy, float sx, float isy,
-                                                                   float isx, int rows, int strips, int pf) {
+                                                                   float isx, int rows, int strips) {
   const unsigned CV = static_cast<unsigned>(dx.c) >> 3;
   const unsigned total = 1u * dx.n * strips * dx.w * CV;
+  const unsigned osh = static_cast<unsigned>(dout.sh);  // element strides of one image fit 32 bits (checked on the host)
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     unsigned t, cv;
     split_cv(dx, i, t, cv);
@@ -138,46 +145,57 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_bwd_kernel(View dout, Vie
     const int n = static_cast<int>(t / strips);
     int ox[NT];
     float wx[NT];
-    const int nx = gather_taps<NT>(sx, isx, dx.w, dout.w, ix, ox, wx);
-    const __nv_bfloat16* src = dout.p + n * dout.sn + cv * 8;
+    gather_taps<NT>(sx, isx, dx.w, dout.w, ix, ox, wx);
+    unsigned toff[NT];
+#pragma unroll
+    for (int b = 0; b < NT; ++b) toff[b] = static_cast<unsigned>(ox[b]) * static_cast<unsigned>(dout.sw) + cv * 8;
     __nv_bfloat16* dst = dx.p + n * dx.sn + ix * dx.sw + cv * 8;
     const int ra = s * rows, rb = min(dx.h, ra + rows);  // owned input rows [ra, rb)
-    const int lo = max(0, static_cast<int>(floorf((ra - 1) * isy)) - 1);
-    const int hi = min(dout.h - 1, static_cast<int>(ceilf(rb * isy)) + 1);
+    // output rows [lo, hi] = those whose stencil (y0, y1) meets [ra, rb): conservative bounds, then exact
+    int lo = max(0, static_cast<int>(floorf((ra - 1) * isy)) - 1);
+    int hi = min(dout.h - 1, static_cast<int>(ceilf(rb * isy)) + 1);
+    {
+      int y0, y1;
+      float l0, l1;
+      for (;; ++lo) {
+        src_index(sy, lo, dx.h, y0, y1, l0, l1);
+        if (y1 >= ra || lo >= hi) break;
+      }
+      for (;; --hi) {
+        src_index(sy, hi, dx.h, y0, y1, l0, l1);
+        if (y0 < rb || hi <= lo) break;
+      }
+    }
+    const __nv_bfloat16* rowp = dout.p + n * dout.sn + static_cast<long long>(lo) * dout.sh;
     float A[8], B[8];  // accumulators of input rows r and r + 1
 #pragma unroll
     for (int j = 0; j < 8; ++j) A[j] = B[j] = 0.f;
     int r = ra - 1;
-    for (int oy = lo; oy <= hi; ++oy) {
+    for (int oy = lo; oy <= hi; ++oy, rowp += osh) {
+      uint4 u[NT];
+#pragma unroll
+      for (int b = 0; b < NT; ++b) u[b] = ldg16(rowp + toff[b]);  // unused slots re-read tap 0 with weight 0
       int y0, y1;
       float ly0, ly1;
       src_index(sy, oy, dx.h, y0, y1, ly0, ly1);
-      if (y1 < ra) continue;
-      if (y0 >= rb) break;
-      while (r < y0) {  // rows above y0 are complete
+      if (y0 != r) {  // row r is complete (y0 == r + 1; at the very first row possibly further: nothing owned lies between)
         if (r >= ra) stg16(dst + r * dx.sh, pack8(A));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          A[j] = B[j];
+          A[j] = y0 == r + 1 ? B[j] : 0.f;
           B[j] = 0.f;
         }
-        ++r;
+        r = y0;
       }
-      const __nv_bfloat16* rowp = src + oy * dout.sh;
-      if (pf > 0 && oy + pf <= hi) {  // the iterations are dependent (one row of taps in flight per thread): keep `pf`
-        const __nv_bfloat16* ahead = rowp + pf * dout.sh;  // further rows of DRAM requests outstanding through L2
-#pragma unroll
-        for (int b = 0; b < NT; ++b)
-          if (b < nx) prefetch_l2(ahead + ox[b] * dout.sw);
-      }
-      uint4 u[NT];
-#pragma unroll
-      for (int b = 0; b < NT; ++b) u[b] = b < nx ? ldg16(rowp + ox[b] * dout.sw) : make_uint4(0u, 0u, 0u, 0u);
       float g[8];
+      {
+        float v[8];
+        unpack8(u[0], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        for (int j = 0; j < 8; ++j) g[j] = wx[0] * v[j];
+      }
 #pragma unroll
-      for (int b = 0; b < NT; ++b) {
+      for (int b = 1; b < NT; ++b) {
         float v[8];
         unpack8(u[b], v);
 #pragma unroll
@@ -279,17 +297,12 @@ extern "C" int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream) {
   long long total = 1LL * dx.n * strips * dx.w * cv;
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int dbg_smem = -1;  // experiment (CVB_BILINEAR_SMEM bytes): would a shared-memory kernel still co-run with the wgrad CTAs?
-  if (dbg_smem < 0) {
-    const char* e = getenv("CVB_BILINEAR_SMEM");
-    dbg_smem = e ? atoi(e) : 0;
-  }
+  CVB_REQUIRE(1LL * dout.h * dout.sh < (1LL << 31), CVB_ERR_UNSUPPORTED,
+              "bilinear2x_bwd: one image of dout exceeds 32-bit element offsets");
   if (max_adjoint_taps(dx.w, dout.w) <= 4)
-    bilinear2x_bwd_kernel<4><<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
-                                                              prefetch_rows());
+    bilinear2x_bwd_kernel<4><<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips);
   else
-    bilinear2x_bwd_kernel<6><<<grid, kThreads, dbg_smem, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips,
-                                                              prefetch_rows());
+    bilinear2x_bwd_kernel<6><<<grid, kThreads, 0, st>>>(to_dev(dout), to_dev(dx), sy, sx, isy, isx, rows, strips);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
