@@ -485,54 +485,99 @@ __device__ __forceinline__ int item_parts(const WgradParams& p, int item) {
 // out[co][ci][tap] = sum over the parts s of the item that owns the element of ws[s][tap][ci][co].  ONE kernel for the
 // split-K reduction and the transposition to nn.Conv2d.weight.grad's OIHW layout (round 1 ran two, 46 launches per UNet
 // step). A block owns a brick of 32 co x BCI ci x all taps: it sums the parts with coalesced 128-byte reads (co fastest;
-// the part count is a property of the (tap, ci) row: a 32-wide co run never straddles a co tile), transposes the brick
-// through shared memory and writes runs of BCI*taps contiguous floats per co row. BCI shrinks for small layers so that
-// the grid still fills the GPU. Deterministic: fixed summation order, no atomics.
+// the part count is a property of the (tap group, ci tile, co tile) item and a brick lies inside one ci tile and one co
+// tile: at most n_tap_groups items per brick, their part counts are worked out once per block), transposes the brick
+// through shared memory and writes runs of BCI*taps contiguous floats per co row. The brick is kept in OIHW order
+// ([ci][tap] rows of 33 floats) so that both the stores of the first phase and the loads of the second are free of bank
+// conflicts and the second phase needs no index arithmetic (the [tap][ci] order cost 8-way conflicts and a division per
+// element). BCI shrinks for small layers so that the grid still fills the GPU. Deterministic: fixed summation order, no
+// atomics.
+// Items that stream-K cut into many parts (the cout = 64 layers: ONE item per 64 input channels, a part per SM) would make
+// a thread walk 74-148 parts one dependent load after another: there the block's warps split the PARTS between them
+// (`ps` part groups, chosen per block from its items' part counts, at most ps_max = what the host sized the brick
+// buffer for) and the second phase adds the groups up.
+template <int TAPS>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, const WgradParams p, int BN,
-                                                           int cout, int cin_eff, int x_c, int bci,
+                                                           int cout, int cin_eff, int x_c, int bci, int ps_max,
                                                            float* __restrict__ out) {
-  extern __shared__ float tile[];  // [taps][bci][33]
-  const int taps = p.taps, cin_pad = p.cin_pad, cout_pad = p.cout_pad;
+  extern __shared__ float tile[];  // [ps][bci][TAPS][33]
+  __shared__ int s_parts[16];
+  const int cin_pad = p.cin_pad, cout_pad = p.cout_pad;
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * bci;
-  const int tx = threadIdx.x & 31;
-  const long long split_stride = 1LL * taps * cin_pad * cout_pad;
-  const int elems = taps * bci;  // (tap, i) pairs, each a 32-wide co row
-  // 16-byte loads: a thread owns 4 consecutive co of one (tap, ci) row; a warp covers 4 rows x 128 bytes per load, the
-  // block 32 rows per iteration, up to four parts of a row in flight
-  const int q = tx & 7, rsub = tx >> 3;
-  for (int e = (threadIdx.x >> 5) * 4 + rsub; e < elems; e += 32) {
-    const int tap = e / bci, i = e - tap * bci;
-    const int ci = ci0 + i, co = co0 + q * 4;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    if (ci < cin_pad && ci < x_c && co < cout_pad) {
-      const int item = ((tap / p.T) * p.n_ci_tiles + ci / (64 * p.CM)) * p.n_co_tiles + co0 / BN;
-      const int parts = item_parts(p, item);
-      const float4* src = reinterpret_cast<const float4*>(ws + (1LL * tap * cin_pad + ci) * cout_pad + co);
-      const long long ss = split_stride >> 2;
-      auto add = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
-      int s = 0;
-      for (; s + 3 < parts; s += 4) {
-        const float4 v0 = __ldcs(src + s * ss), v1 = __ldcs(src + (s + 1) * ss), v2 = __ldcs(src + (s + 2) * ss),
-                     v3 = __ldcs(src + (s + 3) * ss);
-        add(a0, v0); add(a1, v1); add(a2, v2); add(a3, v3);
-      }
-      for (; s < parts; ++s) add(a0, __ldcs(src + s * ss));
-    }
-    float* t = tile + (tap * bci + i) * 33 + q * 4;
-    t[0] = (a0.x + a1.x) + (a2.x + a3.x);
-    t[1] = (a0.y + a1.y) + (a2.y + a3.y);
-    t[2] = (a0.z + a1.z) + (a2.z + a3.z);
-    t[3] = (a0.w + a1.w) + (a2.w + a3.w);
+  const int tx = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < p.n_tap_groups && threadIdx.x < 16) {
+    const int item = (static_cast<int>(threadIdx.x) * p.n_ci_tiles + ci0 / (64 * p.CM)) * p.n_co_tiles + co0 / BN;
+    s_parts[threadIdx.x] = item_parts(p, item);
   }
   __syncthreads();
-  const int row_elems = bci * taps;  // contiguous in OIHW for a fixed co
-  for (int j = threadIdx.x >> 5; j < 32; j += 8) {
-    const int co = co0 + j;
-    if (co >= cout) continue;
+  int max_parts = 1;
+  for (int g = 0; g < p.n_tap_groups && g < 16; ++g) max_parts = max(max_parts, s_parts[g]);
+  int ps = max_parts >= 32 ? 8 : (max_parts >= 8 ? 4 : (max_parts >= 3 ? 2 : 1));
+  if (ps > ps_max) ps = ps_max;
+  const int pg = warp % ps, wr = warp / ps, row_step = (8 / ps) * 4;  // part group / row group of this warp
+  const long long ss = (1LL * TAPS * cin_pad * cout_pad) >> 2;  // part stride in float4
+  const int elems = TAPS * bci;  // (tap, i) pairs, each a 32-wide co row
+  const int gstride = elems * 33;
+  // 16-byte loads: a thread owns 4 consecutive co of one (tap, ci) row; a warp covers 4 rows x 128 bytes per load; three
+  // rows per thread are in flight, then up to four further parts of a row
+  const int q = tx & 7, rsub = tx >> 3;
+  const int co = co0 + q * 4;
+  auto add = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
+  for (int e0 = wr * 4 + rsub; e0 < elems; e0 += 3 * row_step) {
+    float4 acc[3];
+    const float4* src[3];
+    int parts[3], slot[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = e0 + u * row_step;
+      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      parts[u] = 0;
+      slot[u] = -1;
+      src[u] = nullptr;
+      if (e < elems) {
+        const int tap = e / bci, i = e - tap * bci;
+        const int ci = ci0 + i;
+        slot[u] = pg * gstride + (i * TAPS + tap) * 33 + q * 4;
+        if (ci < cin_pad && ci < x_c && co < cout_pad) {
+          parts[u] = s_parts[tap / p.T];
+          src[u] = reinterpret_cast<const float4*>(ws + (1LL * tap * cin_pad + ci) * cout_pad + co);
+          if (pg < parts[u]) acc[u] = __ldcs(src[u] + pg * ss);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (parts[u] > pg + ps) {  // split items: this group's remaining parts, four in flight
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, a3 = a1;
+        int sidx = pg + ps;
+        for (; sidx + 3 * ps < parts[u]; sidx += 4 * ps) {
+          const float4 v0 = __ldcs(src[u] + sidx * ss), v1 = __ldcs(src[u] + (sidx + ps) * ss),
+                       v2 = __ldcs(src[u] + (sidx + 2 * ps) * ss), v3 = __ldcs(src[u] + (sidx + 3 * ps) * ss);
+          add(acc[u], v0); add(a1, v1); add(a2, v2); add(a3, v3);
+        }
+        for (; sidx < parts[u]; sidx += ps) add(acc[u], __ldcs(src[u] + sidx * ss));
+        add(a1, a3);
+        add(acc[u], a2);
+        add(acc[u], a1);
+      }
+      if (slot[u] >= 0) {
+        float* t = tile + slot[u];
+        t[0] = acc[u].x; t[1] = acc[u].y; t[2] = acc[u].z; t[3] = acc[u].w;
+      }
+    }
+  }
+  __syncthreads();
+  // OIHW: for a fixed co the brick's (ci, tap) elements are contiguous, in the order the brick is stored
+  const int ci_n = min(bci, cin_eff - ci0);
+  const int row_elems = ci_n * TAPS;
+  for (int j = warp; j < 32; j += 8) {
+    const int c = co0 + j;
+    if (c >= cout) continue;
+    float* dst = out + (1LL * c * cin_eff + ci0) * TAPS;
     for (int e = tx; e < row_elems; e += 32) {
-      const int i = e / taps, tap = e - i * taps;
-      const int ci = ci0 + i;
-      if (ci < cin_eff) out[(1LL * co * cin_eff + ci) * taps + tap] = tile[(tap * bci + i) * 33 + j];
+      float v = tile[e * 33 + j];
+      for (int g = 1; g < ps; ++g) v += tile[g * gstride + e * 33 + j];
+      dst[e] = v;
     }
   }
 }
@@ -752,13 +797,18 @@ extern "C" int cvb_conv3x3_wgrad(cvb_view x, cvb_view dy, int taps, float* dw, i
   }
   if (rc) return rc;
   }
-  // reduction bricks: shrink the ci extent until the grid has a few hundred blocks
+  // reduction bricks: part groups for items cut into many parts (ps_max * bci <= 32 bounds the brick buffer), then shrink
+  // the ci extent until the grid has a few hundred blocks
   const int cin_pad = plan.p.cin_pad, cout_pad = plan.p.cout_pad;
-  int bci = 32;
-  while (bci > 2 && 1LL * ((cout_pad + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
+  const int ps_max = plan.p.slots >= 32 ? 8 : (plan.p.slots >= 8 ? 4 : (plan.p.slots >= 3 ? 2 : 1));
+  int bci = 32 / ps_max;
+  while (bci > 1 && 1LL * ((cout_pad + 31) / 32) * ((cin_pad + bci - 1) / bci) < 2 * sm_count()) bci >>= 1;
   dim3 rgrid((cout_pad + 31) / 32, (x.c + bci - 1) / bci);
-  wgrad_reduce_kernel<<<rgrid, 256, taps * bci * 33 * sizeof(float), st>>>(plan.p.ws, plan.p, plan.BN, cout, cin_eff, x.c, bci,
-                                                                          dw);
+  const size_t rsmem = static_cast<size_t>(ps_max) * taps * bci * 33 * sizeof(float);
+  if (taps == 9)
+    wgrad_reduce_kernel<9><<<rgrid, 256, rsmem, st>>>(plan.p.ws, plan.p, plan.BN, cout, cin_eff, x.c, bci, ps_max, dw);
+  else
+    wgrad_reduce_kernel<1><<<rgrid, 256, rsmem, st>>>(plan.p.ws, plan.p, plan.BN, cout, cin_eff, x.c, bci, ps_max, dw);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
