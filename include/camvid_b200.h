@@ -232,6 +232,10 @@ CVB_API int cvb_pool_code_to_index(const uint8_t* code, int n, int ho, int wo, i
  * nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)  (models/unet.py:25,29)
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream);
+/* The same with the BatchNorm+ReLU of the block that produced the source fused in (ABI 4, cross-layer fusion, the
+ * `BasicConv2d -> UpSample2d` hand-over of models/unet.py:112-147): out = upsample(bf16(relu(y*scale + shift))), bit-identical
+ * to cvb_bn_relu_apply followed by cvb_bilinear2x_fwd; that block's activation is never written. */
+CVB_API int cvb_bn_relu_bilinear2x_fwd(cvb_view y, const float* scale, const float* shift, cvb_view out, void* stream);
 CVB_API int cvb_bilinear2x_bwd(cvb_view dout, cvb_view dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -74,6 +74,7 @@ SIGNATURES = {
     "cvb_maxunpool2x2_bwd": (_I, [View, _P, View, _P]),
     "cvb_pool_code_to_index": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "cvb_bilinear2x_fwd": (_I, [View, View, _P]),
+    "cvb_bn_relu_bilinear2x_fwd": (_I, [View, _P, _P, View, _P]),
     "cvb_bilinear2x_bwd": (_I, [View, View, _P]),
     "cvb_softmax_ce_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _L, _I, _P, _P, _P, _F, _P]),
     "cvb_softmax_ce_nhwc_bf16": (_I, [View, _I, _P, _I, _L, _I, _P, _P, View, _F, _P]),

@@ -53,17 +53,6 @@ inline int check_view(const cvb_view& v, const char* name) {
   return CVB_OK;
 }
 
-// development knob shared by the strip-marching kernels: rows of L2 prefetch distance (CVB_PREFETCH_ROWS, default 4)
-inline int prefetch_rows() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVB_PREFETCH_ROWS");
-    v = e ? atoi(e) : 4;
-    if (v < 0) v = 0;
-  }
-  return v;
-}
-
 inline bool same_shape(const cvb_view& a, const cvb_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }

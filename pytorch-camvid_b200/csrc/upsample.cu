@@ -16,13 +16,24 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
   l0 = 1.f - l1;
 }
 
-// x-interpolated row: lx0 * in[y][x0] + lx1 * in[y][x1] for 8 channels
+// x-interpolated row: lx0 * in[y][x0] + lx1 * in[y][x1] for 8 channels. BN: the source is a raw conv output y and the
+// value interpolated is a = bf16(relu(y*scale + shift)), exactly what cvb_bn_relu_apply would have stored.
+template <bool BN>
 __device__ __forceinline__ void lerp_row(const __nv_bfloat16* p0, const __nv_bfloat16* p1, float lx0, float lx1,
-                                         float (&r)[8]) {
+                                         const float (&sc)[8], const float (&sh)[8], float (&r)[8]) {
   const uint4 ua = ldg16(p0), ub = ldg16(p1);
   float a[8], b[8];
   unpack8(ua, a);
   unpack8(ub, b);
+  if (BN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f);
+      b[j] = fmaxf(fmaf(b[j], sc[j], sh[j]), 0.f);
+    }
+    unpack8(pack8(a), a);
+    unpack8(pack8(b), b);
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = lx0 * a[j] + lx1 * b[j];
 }
@@ -31,14 +42,27 @@ __device__ __forceinline__ void lerp_row(const __nv_bfloat16* p0, const __nv_bfl
 // x-interpolated values of the two source rows in use stay in registers: a source row is fetched once per strip (two
 // 16-byte loads) instead of once per output pixel that touches it -- about one load per store instead of four.
 // Consecutive threads = consecutive channel vectors, then consecutive columns: every access of a warp is one
-// contiguous run.
+// contiguous run. The kernel is bound by HBM WRITES (8 of its 10 bytes per input element are stores; write-only
+// bandwidth is 3.9 TB/s against 5.9 TB/s reading), which is also why the BatchNorm+ReLU of the block
+// that produced the source can ride along for free (BN = true, cross-layer fusion: that block's activation is never
+// written -- nothing else reads it).
+template <bool BN>
 __global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View out, float sy, float sx, int rows,
-                                                                   int strips, int pf) {
+                                                                   int strips, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift) {
   const unsigned CV = static_cast<unsigned>(x.c) >> 3;
   const unsigned total = 1u * out.n * strips * out.w * CV;
+  const unsigned xsh = static_cast<unsigned>(x.sh), osh = static_cast<unsigned>(out.sh);
+  float sc[8], sh[8];
+  unsigned cv_loaded = 0xffffffffu;
   for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
     unsigned t, cv;
     split_cv(out, i, t, cv);
+    if (BN && cv != cv_loaded) {  // a thread keeps its channel group whenever the grid stride is a multiple of C / 8
+      ld8f(scale + cv * 8, sc);
+      ld8f(shift + cv * 8, sh);
+      cv_loaded = cv;
+    }
     const int ox = static_cast<int>(t % out.w);
     t /= out.w;
     const int s = static_cast<int>(t % strips);
@@ -48,32 +72,31 @@ __global__ void __launch_bounds__(kThreads) bilinear2x_fwd_kernel(View x, View o
     src_index(sx, ox, x.w, x0, x1, lx0, lx1);
     const __nv_bfloat16* c0 = x.p + n * x.sn + x0 * x.sw + cv * 8;
     const __nv_bfloat16* c1 = x.p + n * x.sn + x1 * x.sw + cv * 8;
-    __nv_bfloat16* po = out.p + n * out.sn + ox * out.sw + cv * 8;
     float ra[8], rb[8];
     int r = -2;  // source row held in ra; rb holds the row below it (or the same row at the bottom edge)
-    const int oy_end = min(out.h, (s + 1) * rows);
-    for (int oy = s * rows; oy < oy_end; ++oy) {
+    const int oy0 = s * rows, oy_end = min(out.h, oy0 + rows);
+    // running output pointer and 32-bit source-row offsets (one image fits 32-bit element offsets: host check)
+    __nv_bfloat16* po = out.p + n * out.sn + static_cast<long long>(oy0) * out.sh + ox * out.sw + cv * 8;
+    for (int oy = oy0; oy < oy_end; ++oy, po += osh) {
       int y0, y1;
       float ly0, ly1;
       src_index(sy, oy, x.h, y0, y1, ly0, ly1);
       if (y0 != r) {
-        if (pf > 0 && y1 + pf < x.h) {  // the source row needed `pf` source rows from now: start its DRAM fetch
-          prefetch_l2(c0 + (y1 + pf) * x.sh);
-          prefetch_l2(c1 + (y1 + pf) * x.sh);
-        }
         if (y0 == r + 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) ra[j] = rb[j];
         } else {
-          lerp_row(c0 + y0 * x.sh, c1 + y0 * x.sh, lx0, lx1, ra);
+          const unsigned o0 = static_cast<unsigned>(y0) * xsh;
+          lerp_row<BN>(c0 + o0, c1 + o0, lx0, lx1, sc, sh, ra);
         }
-        lerp_row(c0 + y1 * x.sh, c1 + y1 * x.sh, lx0, lx1, rb);
+        const unsigned o1 = static_cast<unsigned>(y1) * xsh;
+        lerp_row<BN>(c0 + o1, c1 + o1, lx0, lx1, sc, sh, rb);
         r = y0;
       }
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = ly0 * ra[j] + ly1 * rb[j];
-      stg16(po + oy * out.sh, pack8(o));
+      stg16(po, pack8(o));
     }
   }
 }
@@ -234,7 +257,7 @@ static int strip_rows(int n, int h, int w, int cv, int want) {
   return rows;
 }
 
-extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
+static int launch_bilinear_fwd(cvb_view x, cvb_view out, const float* scale, const float* shift, void* stream) {
   int rc = check_view(x, "bilinear.x");
   if (rc) return rc;
   rc = check_view(out, "bilinear.out");
@@ -242,6 +265,8 @@ extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   rc = up_shapes_ok(x, out, "bilinear2x_fwd");
   if (rc) return rc;
   CVB_REQUIRE(fits_u32(out), CVB_ERR_UNSUPPORTED, "bilinear2x_fwd: view too large for 32-bit indexing");
+  CVB_REQUIRE(1LL * x.h * x.sh < (1LL << 31) && out.sh < (1LL << 31), CVB_ERR_UNSUPPORTED,
+              "bilinear2x_fwd: one source image exceeds 32-bit element offsets");
   const int cv = out.c / 8;
   const int rows = strip_rows(out.n, out.h, out.w, cv, 16);
   const int strips = (out.h + rows - 1) / rows;
@@ -249,9 +274,21 @@ extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
   const int grid = ew_grid(total, kThreads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float fsy = ac_scale(x.h, out.h), fsx = ac_scale(x.w, out.w);
-  bilinear2x_fwd_kernel<<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips, prefetch_rows());
+  if (scale)
+    bilinear2x_fwd_kernel<true><<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips, scale, shift);
+  else
+    bilinear2x_fwd_kernel<false><<<grid, kThreads, 0, st>>>(to_dev(x), to_dev(out), fsy, fsx, rows, strips, nullptr, nullptr);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
+}
+
+extern "C" int cvb_bilinear2x_fwd(cvb_view x, cvb_view out, void* stream) {
+  return launch_bilinear_fwd(x, out, nullptr, nullptr, stream);
+}
+
+extern "C" int cvb_bn_relu_bilinear2x_fwd(cvb_view y, const float* scale, const float* shift, cvb_view out, void* stream) {
+  CVB_REQUIRE(scale && shift, CVB_ERR_INVALID_ARG, "bn_relu_bilinear2x_fwd: null scale/shift");
+  return launch_bilinear_fwd(y, out, scale, shift, stream);
 }
 
 // largest number of output positions whose stencil touches one input position (same fp32 index math as the kernels)

@@ -36,7 +36,19 @@ FUSE_POOL_BWD_REDUCE = os.environ.get("CVB_FUSE_POOL_BWD", "1") != "0"
 # (cvb_bn_relu_apply_nchw_f32) and the fp32 NCHW gradient of the loss is converted AND reduced for its BatchNorm backward
 # in one pass (cvb_nchw_f32_to_nhwc_bf16_bn_reduce): two full-resolution HBM passes and two launches fewer per step.
 FUSE_BOUNDARY = os.environ.get("CVB_FUSE_BOUNDARY", "1") != "0"
+# UNet: the BatchNorm+ReLU of a block whose activation feeds ONLY a bilinear upsampling (bottleneck, up1-up3 second
+# conv) is applied inside the upsampling kernel (cvb_bn_relu_bilinear2x_fwd); the activation itself is not written.
+FUSE_UPSAMPLE_BN = os.environ.get("CVB_FUSE_UPSAMPLE_BN", "1") != "0"
+# Inspection aid (tests read every block's activation back from the plan): also write the activations that the fusions
+# above make unnecessary.
+MATERIALIZE_ACTIVATIONS = os.environ.get("CVB_MATERIALIZE_ACTIVATIONS", "0") != "0"
 SERIALIZE_TENSOR_KERNELS = os.environ.get("CVB_SERIALIZE_TENSOR", "0") != "0"  # measured: see DESIGN.md knobs
+# The side stream may trail the main stream by WGRAD_LAG blocks: the weight gradient of block k is enqueued after the
+# data gradient of block k + LAG. The backward pass starts and ends with the full-resolution blocks, whose kernels on
+# BOTH streams are HBM-bound (BatchNorm passes, cout = 64 convolutions, the 0.9 GB weight gradients), and spends its
+# middle in the deep layers, where both streams are tensor-bound; a lag shifts the HBM-heavy weight gradients under the
+# deep data gradients and the tensor-bound deep weight gradients under the HBM-bound passes of the last encoder blocks.
+WGRAD_LAG = int(os.environ.get("CVB_WGRAD_LAG", "0"))
 
 
 def narrow_channels(c):
@@ -107,7 +119,8 @@ class Block:
         """Whether this block, as the network's last one, can write the logits / read the loss gradient directly."""
         return FUSE_BOUNDARY and self.ce in (8, 16)
 
-    def forward_train(self, pool_out=None, code=None, logits_out=None):
+    def forward_train(self, pool_out=None, code=None, logits_out=None, defer_apply=False):
+        """defer_apply: the consumer applies this block's BatchNorm+ReLU itself (from y, vec[2], vec[3])."""
         p, bn = self.plan, self.bn
         self._pack_f()
         parts = p.parts_view(self.cout_pad)
@@ -124,6 +137,10 @@ class Block:
             # the network's last block: its activation is the fp32 NCHW tensor the module returns; the bf16 copy in
             # self.a is not written (backward takes the ReLU mask from y)
             ops.bn_relu_apply_nchw(self.y_e, v[2], v[3], logits_out)
+            if MATERIALIZE_ACTIVATIONS:
+                ops.bn_relu_apply(self.y_e, v[2], v[3], self.a_e)
+        elif defer_apply and not MATERIALIZE_ACTIVATIONS:
+            pass
         elif pool_out is not None:
             ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
         else:
@@ -198,13 +215,15 @@ class Block:
             # The side stream picks the weight gradient up AFTER the data gradient: started together the two tensor-bound
             # kernels only split the SMs between them (measured: same finish time as back to back) and the HBM-bound
             # BatchNorm passes of the next block then run alone. Started here, the weight gradient's MMAs run under
-            # those passes (they need no shared memory and co-reside with the wgrad CTAs).
-            ready = torch.cuda.Event()
-            ready.record()
-            p.wstream.wait_event(ready)
-            with torch.cuda.stream(p.wstream):
-                ops.conv3x3_wgrad(self.x, self.dy_w, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
+            # those passes (they need no shared memory and co-reside with the wgrad CTAs). With WGRAD_LAG > 0 it is
+            # queued instead and enqueued LAG blocks later (Plan.drain_wgrads).
+            p.pending_wgrads.append((self, dw))
+            p.drain_wgrads(WGRAD_LAG)
         return fused
+
+    def launch_wgrad(self, dw):
+        p = self.plan
+        ops.conv3x3_wgrad(self.x, self.dy_w, dw, taps=self.taps, workspace=p.workspace, algo_flops=self.flops)
 
 
 class Plan:
@@ -224,8 +243,37 @@ class Plan:
         self.reducer = None  # parallel.GradReducer of the module during a backward pass (data parallelism)
         self.wstream = None  # side stream of the weight-gradient kernels during a backward pass
         self._wstream = None
+        self.pending_wgrads = collections.deque()  # (block, dw) whose weight gradient is not enqueued yet (WGRAD_LAG)
         self.handle = next(_HANDLES)  # how the dispatcher ops below address this plan
         _PLANS[self.handle] = self
+
+    def input_buffer(self, cin):
+        """NHWC bf16 operand of the first convolution and its tap count. Up to 7 input channels (CamVid: 3) the 3x3
+        neighbourhood is gathered into the channel dimension (im2col: K = 9 * cin <= 64 becomes ONE GEMM tap); wider
+        inputs take the ordinary 9-tap path on a 64-channel-padded copy."""
+        self.first_taps = 1 if 9 * cin <= 64 else 9
+        c_mem = min(64, (9 * cin + 15) // 16 * 16) if self.first_taps == 1 else pad64(cin)
+        return self.buf(self.h, self.w, c_mem)
+
+    def load_input(self, x):
+        if self.first_taps == 1:
+            ops.im2col3x3(x, self.cols)
+        else:
+            ops.nchw_to_nhwc(x, self.cols)
+
+    def drain_wgrads(self, keep):
+        """Enqueues the queued weight gradients on the side stream, oldest first, until at most `keep` are left; each
+        starts after everything the main stream has been given so far. A block's gradient range is reported to the
+        data-parallel reducer when its weight gradient is enqueued (the ranges stay in layout order: FIFO)."""
+        while len(self.pending_wgrads) > keep:
+            b, dw = self.pending_wgrads.popleft()
+            ready = torch.cuda.Event()
+            ready.record()
+            self.wstream.wait_event(ready)
+            with torch.cuda.stream(self.wstream):
+                b.launch_wgrad(dw)
+            if self.reducer is not None:
+                self.reducer.ready(b.g_w, b.g_end, also_wait=self.wstream)
 
     def parts_view(self, c):
         rows = self.parts.shape[0]
@@ -340,6 +388,7 @@ class Plan:
             flat = torch.zeros(self.flat_size, device=self.device)  # one memset instead of a fill per conv-bias slice
         if self.reducer is not None:
             self.reducer.begin(flat)
+        self.pending_wgrads.clear()
         if OVERLAP_WGRAD:
             if self._wstream is None:
                 self._wstream = torch.cuda.Stream(device=self.device)
@@ -350,11 +399,13 @@ class Plan:
         return flat
 
     def _done(self, b):
-        if self.reducer is not None:
-            self.reducer.ready(b.g_w, b.g_end, also_wait=self.wstream)
+        # with the side stream on, drain_wgrads reports the range when the block's weight gradient is enqueued
+        if self.reducer is not None and self.wstream is None:
+            self.reducer.ready(b.g_w, b.g_end, also_wait=None)
 
     def _end_backward(self, flat):
         if self.wstream is not None:
+            self.drain_wgrads(0)
             torch.cuda.current_stream(self.device).wait_stream(self.wstream)
             self.wstream = None
         if self.reducer is not None:
@@ -377,7 +428,7 @@ class UNetPlan(Plan):
             hs.append(hs[-1] // 2)
             ws.append(ws[-1] // 2)
         ch = [64, 128, 256, 512, 1024]
-        self.cols = self.buf(h, w, min(64, (9 * m.input_channels + 15) // 16 * 16))  # im2col of the input: 27 real channels of 32
+        self.cols = self.input_buffer(m.input_channels)  # CamVid: im2col of the input, 27 real channels of 32
         # concat buffers at levels 0..3: channels [0, ch[l]) = upsampled branch, [ch[l], 2 ch[l]) = encoder skip
         self.cat = [self.buf(hs[l], ws[l], 2 * ch[l], zero=True) for l in range(4)]
         self.dcat = [self.buf(hs[l], ws[l], 2 * ch[l]) for l in range(4)]
@@ -389,7 +440,7 @@ class UNetPlan(Plan):
             mid = self.buf(hs[l], ws[l], ch[l])
             self.enc_mid.append(mid)
             self.d_enc_mid.append(torch.empty_like(mid))
-            b0 = self.add(f"down{l + 1}.0", downs[l][0].conv, x, mid, taps=1 if l == 0 else 9)
+            b0 = self.add(f"down{l + 1}.0", downs[l][0].conv, x, mid, taps=self.first_taps if l == 0 else 9)
             if l < 4:
                 out = self.cat[l][..., ch[l]:]
                 pooled = self.buf(hs[l + 1], ws[l + 1], ch[l])
@@ -434,23 +485,33 @@ class UNetPlan(Plan):
 
     def forward(self, x, train):
         self.pack_weights()
-        ops.im2col3x3(x, self.cols)
+        self.load_input(x)
+        fuse_up = train and FUSE_UPSAMPLE_BN
         for l, (b0, b1) in enumerate(self.enc):
             if train:
                 b0.forward_train()
                 if l < 4:
                     b1.forward_train(pool_out=self.pooled[l], code=self.codes[l])
                 else:
-                    b1.forward_train()
+                    b1.forward_train(defer_apply=fuse_up)  # the bottleneck feeds only the first upsampling
             else:
                 b0.forward_eval()
                 b1.forward_eval()
                 if l < 4:
                     ops.maxpool2x2(b1.a, self.pooled[l])
-        for d in self.dec:
-            ops.bilinear2x(d["src"], d["up"])
+        prev = self.enc[4][1]  # the block whose activation is upsampled
+        for i, d in enumerate(self.dec):
+            if fuse_up:
+                ops.bn_relu_bilinear2x(prev.y_e, prev.vec[2], prev.vec[3], d["up"])
+            else:
+                ops.bilinear2x(d["src"], d["up"])
             for b in (d["bu"], d["b0"], d["b1"]):
-                b.forward_train() if train else b.forward_eval()
+                if not train:
+                    b.forward_eval()
+                else:
+                    # up1-up3: the second conv's activation feeds only the next upsampling
+                    b.forward_train(defer_apply=fuse_up and b is d["b1"] and i < len(self.dec) - 1)
+            prev = d["b1"]
         if train:
             logits = self._logits_train(self.b_out)
             self._bump_batches_tracked()
@@ -510,7 +571,7 @@ class SegNetPlan(Plan):
         self.class_num = m.class_num
         encs = [m.encoder1, m.encoder2, m.encoder3, m.encoder4, m.encoder5]
         decs = [m.decoder5, m.decoder4, m.decoder3, m.decoder2, m.decoder1]
-        self.cols = self.buf(h, w, min(64, (9 * m.input_channels + 15) // 16 * 16))  # im2col of the input: 27 real channels of 32
+        self.cols = self.input_buffer(m.input_channels)  # CamVid: im2col of the input, 27 real channels of 32
         self.stages = []  # encoder stages: blocks, activations, pooled, code
         x = self.cols
         ch_, cw_ = h, w
@@ -518,7 +579,8 @@ class SegNetPlan(Plan):
             blocks, acts, dacts = [], [], []
             for j, bc in enumerate(seq):
                 a = self.buf(ch_, cw_, pad64(bc.conv.out_channels))
-                blocks.append(self.add(f"encoder{s + 1}.{j}", (bc.conv, bc.bn), x, a, taps=1 if (s == 0 and j == 0) else 9))
+                blocks.append(self.add(f"encoder{s + 1}.{j}", (bc.conv, bc.bn), x, a,
+                                       taps=self.first_taps if (s == 0 and j == 0) else 9))
                 acts.append(a)
                 dacts.append(torch.empty_like(a))
                 x = a
@@ -553,7 +615,7 @@ class SegNetPlan(Plan):
 
     def forward(self, x, train):
         self.pack_weights()
-        ops.im2col3x3(x, self.cols)
+        self.load_input(x)
         for st in self.stages:
             bl = st["blocks"]
             for j, b in enumerate(bl):
@@ -886,8 +948,6 @@ def _check_input(x, channels, what):
 def run_module(module, plan_cls, x):
     """Shared forward of the drop-in modules: x fp32 NCHW CUDA -> logits fp32 NCHW."""
     _check_input(x, module.input_channels, type(module).__name__)
-    if x.shape[1] * 9 > 64:
-        raise RuntimeError("input_channels > 7 is not supported by the first-layer im2col kernel")
     if x.shape[2] < 32 or x.shape[3] < 32:
         raise RuntimeError("input must be at least 32x32 (five 2x2 poolings)")
     x = x.detach().float().contiguous()

@@ -354,6 +354,13 @@ def bilinear2x(x, out):
     return out
 
 
+def bn_relu_bilinear2x(y, scale, shift, out):
+    """out = upsample2x(bf16(relu(y*scale + shift))): the producer block's BatchNorm+ReLU fused into the upsampling."""
+    _call("bn_relu_bilinear2x_fwd", 1, _nbytes(y, out), _lib.load().cvb_bn_relu_bilinear2x_fwd, view(y), _ptr(scale),
+          _ptr(shift), view(out), _stream())
+    return out
+
+
 def bilinear2x_bwd(dout, dx):
     _call("bilinear2x_bwd", 1, _nbytes(dout, dx), _lib.load().cvb_bilinear2x_bwd, view(dout), view(dx), _stream())
     return dx

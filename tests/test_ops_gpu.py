@@ -405,6 +405,21 @@ def test_bilinear2x(ops, cuda, n, h, w, c):
     assert rel_err(to_nchw_f32(dx), dx_ref) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 5, 7, 64), (1, 22, 30, 1024), (2, 45, 60, 512), (1, 1, 3, 64), (2, 9, 11, 24)])
+def test_bilinear2x_fused_with_producer_bn_relu_is_bit_identical(ops, cuda, n, h, w, c):
+    """cvb_bn_relu_bilinear2x_fwd == cvb_bn_relu_apply + cvb_bilinear2x_fwd (the activation rounded to bf16 in between)."""
+    y = _rand((n, h, w, c), cuda, 80).to(torch.bfloat16)
+    scale = (torch.rand(c, device=cuda) + 0.5) * torch.where(torch.rand(c, device=cuda) < 0.2, -1.0, 1.0)
+    shift = torch.randn(c, device=cuda) * 0.3
+    a = torch.empty_like(y)
+    ops.bn_relu_apply(y, scale, shift, a)
+    want = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=cuda)
+    ops.bilinear2x(a, want)
+    got = torch.full_like(want, float("nan"))
+    ops.bn_relu_bilinear2x(y, scale, shift, got)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("n,h,w,c", [(2, 16, 24, 64), (1, 45, 61, 128), (3, 11, 15, 1024), (2, 9, 8, 16)])
 @pytest.mark.parametrize("mode", ["unet", "segnet"])
 def test_maxpool_bwd_fused_with_bn_reduce_is_bit_identical(ops, cuda, n, h, w, c, mode):
