@@ -172,11 +172,14 @@ CVB_API int cvb_bn_stats(cvb_view y, float* partials, int rows, void* stream);
 CVB_API int cvb_bn_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
                     const float* beta, const float* conv_bias, float* running_mean, float* running_var,
                     float momentum, float eps, float* mean, float* invstd, float* scale, float* shift, void* stream);
-/* a = relu(y*scale + shift). */
-CVB_API int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, void* stream);
+/* a = relu(y*scale + shift).
+ * `reverse` (ABI 4, here and in the two backward passes below): != 0 walks the tensor from its last pixel to its first --
+ * same result, different visiting order, for callers who know which end of the tensor the previous kernel left in L2
+ * (the drop-in modules pass 0: measured neutral at their sizes). */
+CVB_API int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, int reverse, void* stream);
 /* Backward pass 1: g = da * [y*scale+shift > 0]; partials fp32 [rows][2][c] of (sum g, sum g*y). */
 CVB_API int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scale, const float* shift, float* partials,
-                           int rows, void* stream);
+                           int rows, int reverse, void* stream);
 /* Backward finalize: dgamma, dbeta (fp32 [c]) and the per-channel coefficients (coef fp32 [3][c_pad]) with
  * dy = g*coef0 + y*coef1 + coef2 used by cvb_bn_relu_bwd_apply. */
 CVB_API int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c_pad, int64_t count, const float* gamma,
@@ -196,7 +199,7 @@ CVB_API int cvb_nchw_f32_to_nhwc_bf16_bn_reduce(const float* src, int c_src, cvb
                                         const float* shift, float* partials, int rows, void* stream);
 /* Backward pass 2: dy = (da*[a>0])*coef0 + y*coef1 + coef2  (bf16 view). */
 CVB_API int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale, const float* shift, const float* coef,
-                          cvb_view dy, void* stream);
+                          cvb_view dy, int reverse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MaxPool2d(2,2) with indices / MaxUnpool2d(2)  (models/unet.py:92, models/segnet.py:79-80).

@@ -60,12 +60,12 @@ SIGNATURES = {
     "cvb_conv3x3_wgrad": (_I, [View, View, _I, _P, _I, _I, _P, _L, _P]),
     "cvb_bn_stats": (_I, [View, _P, _I, _P]),
     "cvb_bn_finalize": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
-    "cvb_bn_relu_apply": (_I, [View, _P, _P, View, _P]),
-    "cvb_bn_relu_bwd_reduce": (_I, [View, View, _P, _P, _P, _I, _P]),
+    "cvb_bn_relu_apply": (_I, [View, _P, _P, View, _I, _P]),
+    "cvb_bn_relu_bwd_reduce": (_I, [View, View, _P, _P, _P, _I, _I, _P]),
     "cvb_bn_relu_apply_nchw_f32": (_I, [View, _P, _P, _P, _I, _P]),
     "cvb_nchw_f32_to_nhwc_bf16_bn_reduce": (_I, [_P, _I, View, View, _P, _P, _P, _I, _P]),
     "cvb_bn_bwd_finalize": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
-    "cvb_bn_relu_bwd_apply": (_I, [View, View, _P, _P, _P, View, _P]),
+    "cvb_bn_relu_bwd_apply": (_I, [View, View, _P, _P, _P, View, _I, _P]),
     "cvb_maxpool2x2_fwd": (_I, [View, View, _P, _P]),
     "cvb_bn_relu_maxpool2x2_fwd": (_I, [View, _P, _P, View, View, _P, _P]),
     "cvb_maxpool2x2_bwd": (_I, [View, _P, View, View, _I, _P]),

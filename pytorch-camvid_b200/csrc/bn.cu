@@ -12,10 +12,13 @@ constexpr int kThreads = 256;
 //   MODE 0: (sum y, sum y^2)                         -- batch statistics
 //   MODE 1: g = da*[y*scale+shift > 0]; (sum g, sum g*y) -- BatchNorm+ReLU backward reduction
 // ---------------------------------------------------------------------------------------------------------------
+// reverse != 0: pixels are visited from the last to the first (an experiment in L2 reuse -- the tensors these passes read
+// were just written front to back and only their END can still be cached; measured neutral). The
+// partial sums are the same numbers either way up to fp32 summation order.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
-                                                              float* __restrict__ partials) {
+                                                              float* __restrict__ partials, int reverse) {
   __shared__ float red[kThreads * 2];
   const int CV = y.c >> 3;
   const int ppb = kThreads / CV;  // pixels handled per block iteration (CV divides kThreads, checked on host)
@@ -31,9 +34,10 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(View y, View da, co
     ld8f(shift + cv * 8, sh);
   }
   const unsigned step = gridDim.x * ppb;
-  for (unsigned pix = blockIdx.x * ppb + pl; pix < npix; pix += 2 * step) {
-    const unsigned pix2 = pix + step;
-    const bool has2 = pix2 < npix;
+  for (unsigned it = blockIdx.x * ppb + pl; it < npix; it += 2 * step) {
+    const bool has2 = it + step < npix;
+    const unsigned pix = reverse ? npix - 1u - it : it;
+    const unsigned pix2 = has2 ? (reverse ? npix - 1u - (it + step) : it + step) : pix;
     // all loads of both pixels are issued before the arithmetic
     const uint4 uy = ldg16(y.p + poff(y, pix) + cv * 8);
     uint4 uy2 = make_uint4(0, 0, 0, 0), ud = uy2, ud2 = uy2;
@@ -213,13 +217,14 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int rows, int c, int 
 // into registers (HOIST); otherwise they are re-read from L1 per element.
 template <bool HOIST>
 __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(View y, View a, const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift) {
+                                                                  const float* __restrict__ shift, int reverse) {
   const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
   const unsigned stride = gridDim.x * kThreads;
   float sc[8], sh[8];
   if (HOIST) {
     unsigned pix0, cv0;
-    split_cv(y, blockIdx.x * kThreads + threadIdx.x, pix0, cv0);
+    const unsigned i0 = blockIdx.x * kThreads + threadIdx.x;
+    split_cv(y, reverse ? total - 1u - (i0 < total ? i0 : 0u) : i0, pix0, cv0);
     ld8f(scale + cv0 * 8, sc);
     ld8f(shift + cv0 * 8, sh);
   }
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(View y, View a,
       const unsigned iq = i + q * stride;
       pix[q] = 0xffffffffu;
       if (iq < total) {
-        split_cv(y, iq, pix[q], cv[q]);
+        split_cv(y, reverse ? total - 1u - iq : iq, pix[q], cv[q]);
         u[q] = ldg16(y.p + poff(y, pix[q]) + cv[q] * 8);
       }
     }
@@ -256,13 +261,15 @@ template <bool HOIST>
 __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, View y, View dy,
                                                                       const float* __restrict__ scale,
                                                                       const float* __restrict__ shift,
-                                                                      const float* __restrict__ coef, int c_pad) {
+                                                                      const float* __restrict__ coef, int c_pad,
+                                                                      int reverse) {
   const unsigned total = static_cast<unsigned>(y.n) * y.h * y.w * (y.c >> 3);
   const unsigned stride = gridDim.x * kThreads;
   float sc[8], sh[8], c0[8], c1[8], c2[8];
   if (HOIST) {
     unsigned pix0, cv0;
-    split_cv(y, blockIdx.x * kThreads + threadIdx.x, pix0, cv0);
+    const unsigned i0 = blockIdx.x * kThreads + threadIdx.x;
+    split_cv(y, reverse ? total - 1u - (i0 < total ? i0 : 0u) : i0, pix0, cv0);
     ld8f(scale + cv0 * 8, sc);
     ld8f(shift + cv0 * 8, sh);
     ld8f(coef + cv0 * 8, c0);
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) bn_relu_bwd_apply_kernel(View da, Vi
       const unsigned iq = i + q * stride;
       pix[q] = 0xffffffffu;
       if (iq < total) {
-        split_cv(y, iq, pix[q], cv[q]);
+        split_cv(y, reverse ? total - 1u - iq : iq, pix[q], cv[q]);
         uy[q] = ldg16(y.p + poff(y, pix[q]) + cv[q] * 8);
         ud[q] = ldg16(da.p + poff(da, pix[q]) + cv[q] * 8);
       }
@@ -433,13 +440,13 @@ extern "C" int cvb_bn_stats(cvb_view y, float* partials, int rows, void* stream)
   if (rc) return rc;
   View vy = to_dev(y);
   bn_reduce_kernel<0><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      vy, vy, nullptr, nullptr, partials);
+      vy, vy, nullptr, nullptr, partials, 0);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
 
 extern "C" int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scale, const float* shift,
-                                      float* partials, int rows, void* stream) {
+                                      float* partials, int rows, int reverse, void* stream) {
   int rc = check_view(y, "bn_bwd_reduce.y");
   if (rc) return rc;
   rc = check_view(da, "bn_bwd_reduce.da");
@@ -450,7 +457,7 @@ extern "C" int cvb_bn_relu_bwd_reduce(cvb_view da, cvb_view y, const float* scal
   rc = reduce_launch_cfg(y, rows, &grid);
   if (rc) return rc;
   bn_reduce_kernel<1><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      to_dev(y), to_dev(da), scale, shift, partials);
+      to_dev(y), to_dev(da), scale, shift, partials, reverse);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
@@ -485,7 +492,8 @@ extern "C" int cvb_bn_bwd_finalize(const float* partials, int rows, int c, int c
   return CVB_OK;
 }
 
-extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, void* stream) {
+extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* shift, cvb_view a, int reverse,
+                                 void* stream) {
   int rc = check_view(y, "bn_relu_apply.y");
   if (rc) return rc;
   rc = check_view(a, "bn_relu_apply.a");
@@ -496,15 +504,17 @@ extern "C" int cvb_bn_relu_apply(cvb_view y, const float* scale, const float* sh
   long long total = 1LL * y.n * y.h * y.w * (y.c / 8);
   const int grid = ew_grid((total + 3) / 4, kThreads);
   if (kThreads % (y.c / 8) == 0)
-    bn_relu_apply_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift);
+    bn_relu_apply_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift,
+                                                                                          reverse);
   else
-    bn_relu_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift);
+    bn_relu_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(y), to_dev(a), scale, shift,
+                                                                                           reverse);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }
 
 extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale, const float* shift,
-                                     const float* coef, cvb_view dy, void* stream) {
+                                     const float* coef, cvb_view dy, int reverse, void* stream) {
   int rc = check_view(y, "bn_bwd_apply.y");
   if (rc) return rc;
   rc = check_view(da, "bn_bwd_apply.da");
@@ -518,10 +528,10 @@ extern "C" int cvb_bn_relu_bwd_apply(cvb_view da, cvb_view y, const float* scale
   const int grid = ew_grid((total + 1) / 2, kThreads);
   if (kThreads % (y.c / 8) == 0)
     bn_relu_bwd_apply_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c, reverse);
   else
     bn_relu_bwd_apply_kernel<false><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c);
+        to_dev(da), to_dev(y), to_dev(dy), scale, shift, coef, y.c, reverse);
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

@@ -39,6 +39,14 @@ FUSE_BOUNDARY = os.environ.get("CVB_FUSE_BOUNDARY", "1") != "0"
 # UNet: the BatchNorm+ReLU of a block whose activation feeds ONLY a bilinear upsampling (bottleneck, up1-up3 second
 # conv) is applied inside the upsampling kernel (cvb_bn_relu_bilinear2x_fwd); the activation itself is not written.
 FUSE_UPSAMPLE_BN = os.environ.get("CVB_FUSE_UPSAMPLE_BN", "1") != "0"
+# Visiting order of the BatchNorm passes (same results): each pass reads what the kernel before it just wrote front to
+# back, and of a tensor larger than the 126 MB L2 only the END should still be cached, so a reversed pass could start on
+# cached lines. Measured (tools/order_ab.py, profiles/r02x_order_ab_unet.txt): no gain in any combination (-0.02 ... +0.28
+# ms on a 21.1 ms step, spread of the samples 0.4 ms) -- the L2 does not behave like an LRU stack under these streams.
+# Off; the flag stays in the ABI for callers with other sizes.
+REV_APPLY = os.environ.get("CVB_REV_APPLY", "0") != "0"
+REV_BWD_REDUCE = os.environ.get("CVB_REV_BWD_REDUCE", "0") != "0"
+REV_BWD_APPLY = os.environ.get("CVB_REV_BWD_APPLY", "0") != "0"
 # Inspection aid (tests read every block's activation back from the plan): also write the activations that the fusions
 # above make unnecessary.
 MATERIALIZE_ACTIVATIONS = os.environ.get("CVB_MATERIALIZE_ACTIVATIONS", "0") != "0"
@@ -144,7 +152,7 @@ class Block:
         elif pool_out is not None:
             ops.bn_relu_maxpool2x2(self.y, v[2], v[3], self.a, pool_out, code)
         else:
-            ops.bn_relu_apply(self.y_e, v[2], v[3], self.a_e)
+            ops.bn_relu_apply(self.y_e, v[2], v[3], self.a_e, reverse=REV_APPLY)
         ops.WORK_SCALE = 1.0
 
     def forward_eval(self):
@@ -180,13 +188,13 @@ class Block:
         # (stat_rows of them); an int = another producer did (that many rows)
         rows = p.stat_rows if stats_ready is True else stats_ready
         if stats_ready is False:
-            ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows)
+            ops.bn_relu_bwd_reduce(da, self.y_e, v[2], v[3], parts, p.reduce_rows, reverse=REV_BWD_REDUCE)
             rows = p.reduce_rows
         dgamma = flat[self.g_gamma:self.g_gamma + self.cout]
         dbeta = flat[self.g_beta:self.g_beta + self.cout]
         ops.bn_bwd_finalize(parts, rows, self.cout, self.ce, self.count, self.bn.weight.detach(), v[0],
                             v[1], dgamma, dbeta, self.coef)
-        ops.bn_relu_bwd_apply(da, self.y_e, v[2], v[3], self.coef, self.y_e)  # y now holds dy
+        ops.bn_relu_bwd_apply(da, self.y_e, v[2], v[3], self.coef, self.y_e, reverse=REV_BWD_APPLY)  # y now holds dy
         ops.WORK_SCALE = 1.0
         dw = flat[self.g_w:self.g_w + self.conv.weight.numel()].view_as(self.conv.weight)
         # (conv bias feeds a batch-stat BatchNorm: its gradient is exactly 0 -- the flat buffer starts zeroed)

@@ -259,15 +259,16 @@ def bn_finalize(partials, rows, c, c_pad, count, gamma, beta, conv_bias, running
           eps, _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _stream())
 
 
-def bn_relu_apply(y, scale, shift, a):
+def bn_relu_apply(y, scale, shift, a, reverse=False):
+    """reverse: walk the tensor back to front (same result; see cvb_bn_relu_apply in the header for when that pays)."""
     _call("bn_relu_apply", 1, _nbytes(y, a), _lib.load().cvb_bn_relu_apply, view(y), _ptr(scale), _ptr(shift),
-          view(a), _stream())
+          view(a), int(reverse), _stream())
     return a
 
 
-def bn_relu_bwd_reduce(da, y, scale, shift, partials, rows):
+def bn_relu_bwd_reduce(da, y, scale, shift, partials, rows, reverse=False):
     _call("bn_relu_bwd_reduce", 1, _nbytes(da, y), _lib.load().cvb_bn_relu_bwd_reduce, view(da), view(y), _ptr(scale),
-          _ptr(shift), _ptr(partials), rows, _stream())
+          _ptr(shift), _ptr(partials), rows, int(reverse), _stream())
 
 
 def bn_relu_apply_nchw(y, scale, shift, dst):
@@ -292,9 +293,9 @@ def bn_bwd_finalize(partials, rows, c, c_pad, count, gamma, mean, invstd, dgamma
           _stream())
 
 
-def bn_relu_bwd_apply(da, y, scale, shift, coef, dy):
+def bn_relu_bwd_apply(da, y, scale, shift, coef, dy, reverse=False):
     _call("bn_relu_bwd_apply", 1, _nbytes(da, y, dy), _lib.load().cvb_bn_relu_bwd_apply, view(da), view(y),
-          _ptr(scale), _ptr(shift), _ptr(coef), view(dy), _stream())
+          _ptr(scale), _ptr(shift), _ptr(coef), view(dy), int(reverse), _stream())
     return dy
 
 
