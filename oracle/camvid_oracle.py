@@ -50,7 +50,7 @@ def _cbr_impl(x, sd, conv, bn, train, momentum=0.1, eps=1e-5):
 # conv operands (activations, weights), conv outputs, activations and activation gradients are HELD in bf16 (rounded
 # to nearest-even at the point they would be stored); every sum, statistic, normalisation, interpolation and the loss
 # is fp32, like the reference.  It exists because the network is chaotic at random init (a perturbation grows about
-# x1.2 per conv+BN+ReLU block, tools/precision_sim.py), so ANY bf16 implementation -- including the reference under
+# x1.2 per conv+BN+ReLU block, tests/precision_sim.py), so ANY bf16 implementation -- including the reference under
 # torch autocast -- sits ~1e-1 away from the fp32 logits; the CUDA path is checked tightly against this model and,
 # block by block on identical inputs, against the fp32 reference.
 # ----------------------------------------------------------------------------------------------------------------

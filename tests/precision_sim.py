@@ -1,6 +1,6 @@
 """CPU simulation: how much logit / gradient error do reduced-precision activation roundings cause in the reference
 network at random init?  Straight-through rounding of conv operands (x, w) and conv outputs (y) inside the fp32 oracle.
-    python tools/precision_sim.py unet 2 90 120"""
+    python tests/precision_sim.py unet 2 90 120"""
 import os
 import sys
 

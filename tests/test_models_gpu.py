@@ -7,7 +7,7 @@ per-pixel argmax agreement, per-layer weight gradients within 3e-2 relative (con
 their gradient is mathematically zero and is compared absolutely).
 
 How the tolerances are applied (DESIGN.md "Parity"). Two properties of the reference network at random init, both
-reproduced on the CPU with the reference's own fp32 arithmetic (oracle storage="bf16", tools/precision_sim.py):
+reproduced on the CPU with the reference's own fp32 arithmetic (oracle storage="bf16", tests/precision_sim.py):
   (1) it is chaotic -- a perturbation grows about x1.2 per conv+BN+ReLU block, so bf16 storage of conv operands and
       outputs alone moves the fp32 logits by ~1e-1 (UNet) to ~6e-1 (SegNet: pooling indices flip) and the first-layer
       gradients by ~8e-1; two bf16 runs that differ only in accumulation order diverge the same way;
