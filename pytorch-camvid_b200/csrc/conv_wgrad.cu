@@ -53,6 +53,11 @@ struct WgradParams {
   int wave_item0[4], wave_items[4], wave_grid[4];
   int slots;              // workspace parts per item
   int stages, stage_bytes;
+  // cluster == 2 (conv_wgrad_kernel only): CTAs 2v, 2v + 1 form a cluster and play ONE range of the partition (virtual CTA
+  // v) on two neighbouring ci tiles (2t, 2t + 1) of the same (co tile, tap group): they read the same dy tiles, so each
+  // fetches half of them and multicasts. Items, n_ci_tiles, grids and parts are then counted in virtual CTAs / tile pairs.
+  int cluster;
+  int patch_stride, dy_bytes;  // conv_wgrad_kernel: bytes between the ci chunks of a stage's x patch / its 64-channel dy units
   float* ws;  // [slots][taps][cin_pad][cout_pad]; part k of an item lives in slot k (k < parts of that item)
 };
 
@@ -97,13 +102,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cl = p.cluster;
+  const int crank = cl == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int vcta = cl == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
 
-  // per wave: this CTA's unit range [u_begin, u_end) of the wave's flattened (local item, tile) space
+  // per wave: this (virtual) CTA's unit range [u_begin, u_end) of the wave's flattened (local item, tile) space
 #define CVB_WAVE_RANGE(w)                                                                                         \
   const long long wave_units = 1LL * p.wave_items[w] * p.total_tiles;                                             \
-  const bool in_wave = static_cast<int>(blockIdx.x) < p.wave_grid[w];                                             \
-  const long long u_begin = in_wave ? sk_begin(wave_units, p.wave_grid[w], blockIdx.x) : 0;                       \
-  const long long u_end = in_wave ? sk_begin(wave_units, p.wave_grid[w], blockIdx.x + 1) : 0;                     \
+  const bool in_wave = vcta < p.wave_grid[w];                                                                     \
+  const long long u_begin = in_wave ? sk_begin(wave_units, p.wave_grid[w], vcta) : 0;                             \
+  const long long u_end = in_wave ? sk_begin(wave_units, p.wave_grid[w], vcta + 1) : 0;                           \
   const int item_first = static_cast<int>(u_begin / p.total_tiles);                                               \
   const int item_last = u_end > u_begin ? static_cast<int>((u_end - 1) / p.total_tiles) : item_first - 1;
 
@@ -114,7 +122,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], cl);  // a stage is free when every CTA of the cluster that it was multicast to has consumed it
     }
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
@@ -126,6 +134,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (cl == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled across the cluster
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -140,7 +149,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int litem = item_first; litem <= item_last; ++litem) {
         const int item = p.wave_item0[w] + litem;
         const int co_tile = item % p.n_co_tiles;
-        const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
+        const int ci_tile = ((item / p.n_co_tiles) % p.n_ci_tiles) * cl + crank;
         const long long base = 1LL * litem * p.total_tiles;
         const int tile_begin = static_cast<int>(max(u_begin, base) - base);
         const int tile_end = static_cast<int>(min(u_end, base + p.total_tiles) - base);
@@ -151,14 +160,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const int h0 = (t % p.tiles_h) * p.th;
           const int n0 = t / p.tiles_h;
           uint8_t* sX = smem + stage * p.stage_bytes;
-          uint8_t* sD = sX + p.CM * kWPatchStride;
+          uint8_t* sD = sX + p.CM * p.patch_stride;
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], tx_bytes);
           for (int c = 0; c < p.CM; ++c)
-            tma_load_4d(sX + c * kWPatchStride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
+            tma_load_4d(sX + c * p.patch_stride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
 #pragma unroll
-          for (int j = 0; j < b_units; ++j)
-            tma_load_4d(sD + j * kWDyBytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
+          for (int j = 0; j < b_units; ++j) {
+            if (cl == 1)
+              tma_load_4d(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
+            else if ((j & 1) == crank)  // this CTA's half of the dy tile, delivered to both CTAs
+              tma_load_4d_mcast(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0, 3);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -170,7 +183,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
     const uint32_t x_lo0 = desc_lo(smem_u32(smem), 0);
-    const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * kWPatchStride, kWDyBytes);
+    const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * p.patch_stride, p.dy_bytes);
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
     int stage = 0;
     uint32_t phase = 0;
@@ -193,7 +206,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int ra = p.taps == 9 ? (tap_a / 3) * kWPitch + tap_a % 3 : kWPitch + 1;
         const int rb = p.taps == 9 ? (tap_b / 3) * kWPitch + tap_b % 3 : kWPitch + 2;
         // second atom: the other ci chunk of the same tap (CM == 2) or the next tap's view of the same chunk
-        const uint32_t lbo = p.CM == 2 ? kWPatchStride : static_cast<uint32_t>(rb - ra) * 128;
+        const uint32_t lbo = p.CM == 2 ? static_cast<uint32_t>(p.patch_stride) : static_cast<uint32_t>(rb - ra) * 128;
         acc_lo[j] = static_cast<uint32_t>(ra) * 8 + ((lbo >> 4) << 16);
       }
       const long long base = 1LL * litem * p.total_tiles;
@@ -221,7 +234,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             case 7: if (7 * BN <= 512) issue_tile<BN, 7>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
             default: if (8 * BN <= 512) issue_tile<BN, 8>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
           }
-          umma_commit(&empty[stage]);
+          if (cl == 1) umma_commit(&empty[stage]);
+          else umma_commit_mcast(&empty[stage], 3);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -244,14 +258,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int litem = item_first; litem <= item_last; ++litem, ++seg) {
       const int item = p.wave_item0[w] + litem;
       const int co_tile = item % p.n_co_tiles;
-      const int ci_tile = (item / p.n_co_tiles) % p.n_ci_tiles;
+      const int ci_tile = ((item / p.n_co_tiles) % p.n_ci_tiles) * cl + crank;
       const int tg = item / (p.n_co_tiles * p.n_ci_tiles);
       const int t0 = tg * p.T;
       const int tcount = min(p.T, p.taps - t0);
       const int units = tcount * p.CM;
       const int accs = (units + 1) >> 1;
-      // this CTA's part number within the item = distance from the CTA that owns the item's first unit
-      const int part = static_cast<int>(blockIdx.x) - sk_owner(wave_units, p.wave_grid[w], 1LL * litem * p.total_tiles);
+      // this CTA's part number within the item = distance from the (virtual) CTA that owns the item's first unit
+      const int part = vcta - sk_owner(wave_units, p.wave_grid[w], 1LL * litem * p.total_tiles);
       mbar_wait(tfull, seg & 1);
       tc_fence_after();
       for (int j = 0; j < accs; ++j) {
@@ -290,6 +304,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (cl == 2) cluster_sync_all();  // neither CTA leaves while the peer's multicasts / commits may still target it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -506,7 +521,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * bci;
   const int tx = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < p.n_tap_groups && threadIdx.x < 16) {
-    const int item = (static_cast<int>(threadIdx.x) * p.n_ci_tiles + ci0 / (64 * p.CM)) * p.n_co_tiles + co0 / BN;
+    const int cl = p.cluster > 1 ? p.cluster : 1;  // cluster mode: an item = a PAIR of ci tiles
+    const int item = (static_cast<int>(threadIdx.x) * p.n_ci_tiles + ci0 / (64 * p.CM * cl)) * p.n_co_tiles + co0 / BN;
     s_parts[threadIdx.x] = item_parts(p, item);
   }
   __syncthreads();
@@ -591,6 +607,8 @@ struct WgradPlan {
   long long ws_bytes;
 };
 
+static int wgrad_max_clusters(int BN);
+
 static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan* plan) {
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_wgrad: taps must be 9 or 1 (got %d)", taps);
   CVB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w, CVB_ERR_INVALID_ARG,
@@ -618,6 +636,17 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
         p.th = th;
       }
     }
+  }
+  {
+    // CVB_WGRAD_TH = 8 / 12: force a shorter pixel tile on the layers that would otherwise pipeline only two stages
+    static int th_env = -1;
+    if (th_env < 0) {
+      const char* e = getenv("CVB_WGRAD_TH");
+      th_env = e ? atoi(e) : 0;
+    }
+    if (th_env >= 8 && th_env < p.th && (th_env % 2) == 0 && !(taps == 9 && cout_pad == 64) && cout_pad >= 128 &&
+        cin_pad >= 128)
+      p.th = th_env;
   }
   p.tiles_h = (x.h + p.th - 1) / p.th;
   long long tiles = 1LL * p.tiles_w * p.tiles_h * x.n;
@@ -658,6 +687,7 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
     plan->ws_bytes = 1LL * slots_rs * taps * cin_pad * cout_pad * 4;
     return CVB_OK;
   }
+  p.cluster = 1;
   p.CM = (cin_pad % 128 == 0) ? 2 : 1;
   // accumulators: accs * BN <= 512 TMEM columns, accs <= kMaxAccs; one accumulator = two 64-row atoms
   int max_accs = 512 / BN;
@@ -668,10 +698,34 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.n_tap_groups = (taps + p.T - 1) / p.T;
   p.n_co_tiles = cout_pad / BN;
   p.n_ci_tiles = cin_pad / (64 * p.CM);
-  p.stage_bytes = p.CM * kWPatchStride + (BN / 64) * kWDyBytes;
+  // shared-memory slots of a stage follow the tile height (1 KB granularity: swizzle atoms): shorter tiles = smaller stages
+  // = a deeper pipeline within the same 225 KB
+  p.patch_stride = ((p.th + 2) * kWPitch * 128 + 1023) / 1024 * 1024;
+  p.dy_bytes = p.th * kWTileW * 128;
+  p.stage_bytes = p.CM * p.patch_stride + (BN / 64) * p.dy_bytes;
   p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
+  // Cluster of two along ci (CVB_WGRAD_CLUSTER=1): neighbouring ci tiles of one (co tile, tap group) read the same dy
+  // tiles; as a cluster each fetches half of them and multicasts, which takes 20-30 % off the L2 -> SM fill traffic the
+  // kernel is bound by (45 B/clk per SM is what the fabric delivers when all SMs pull: tools/exp/exp_mma_pair.cu; the
+  // BN = 256 pipeline asks for 54). Needs dy tiles of >= 2 boxes and an even number of ci tiles.
+  int G = sm_count();
+  {
+    static int want = -1;
+    if (want < 0) {
+      const char* e = getenv("CVB_WGRAD_CLUSTER");
+      want = e ? atoi(e) : 0;
+    }
+    if (want && BN >= 128 && (p.n_ci_tiles % 2) == 0 && (G % 2) == 0) {
+      const int pairs = wgrad_max_clusters(BN);
+      if (pairs > 0) {
+        p.cluster = 2;
+        p.n_ci_tiles /= 2;
+        G = pairs < G / 2 ? pairs : G / 2;
+      }
+    }
+  }
   p.items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
   p.total_units = 1LL * p.items * p.total_tiles;
   // Work partition. Stream-K: the (item, pixel tile) space is flattened and cut into equal contiguous ranges, one per
@@ -682,7 +736,6 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   // Waves: item counts that do not divide the SM count well (40, 80, 160 ...) are processed as successive lockstep
   // partitions, e.g. 80 items = 74 items x 2 CTAs, then 6 items x 24 CTAs; per CTA the waves add up to an equal share.
   // CVB_WGRAD_LOCKSTEP=0 falls back to one plain stream-K partition (A/B).
-  const int G = sm_count();
   const char* ls_env = getenv("CVB_WGRAD_LOCKSTEP");
   const bool lockstep = !(ls_env && atoi(ls_env) == 0);
   p.n_waves = 0;
@@ -723,21 +776,70 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
     }
   }
   p.slots = slots;
-  plan->grid = p.grid;
+  plan->grid = p.grid * p.cluster;
   plan->smem = 1024 + p.stages * p.stage_bytes + 256;
   plan->ws_bytes = 1LL * slots * taps * cin_pad * cout_pad * 4;
   return CVB_OK;
 }
 
 template <int BN>
-static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
+static int configure_wgrad() {
   static bool configured = false;
   if (!configured) {
     CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kWgradSmemBudget));
     configured = true;
   }
-  conv_wgrad_kernel<BN><<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
+  return CVB_OK;
+}
+
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int grid, int smem, cudaStream_t st) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = dim3(grid);
+  cfg->blockDim = dim3(kWgradThreads);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = st;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg->attrs = at;
+  cfg->numAttrs = 1;
+}
+
+// How many 2-CTA clusters of the weight-gradient kernel the device runs at once (1 CTA per SM: the two CTAs of a cluster
+// need two free SMs of one GPC); 0 if clusters cannot be used. Asked once per tile width.
+template <int BN>
+static int max_clusters_bn() {
+  static int cached = -1;
+  if (cached < 0) {
+    cached = 0;
+    if (configure_wgrad<BN>() == CVB_OK) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute at[1];
+      cluster_config(&cfg, at, sm_count(), kWgradSmemBudget, nullptr);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_wgrad_kernel<BN>, &cfg) == cudaSuccess) cached = n;
+      else (void)cudaGetLastError();
+    }
+  }
+  return cached;
+}
+
+static int wgrad_max_clusters(int BN) { return BN == 256 ? max_clusters_bn<256>() : (BN == 128 ? max_clusters_bn<128>() : 0); }
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
+  int rc = configure_wgrad<BN>();
+  if (rc) return rc;
+  if (plan.p.cluster == 2) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    cluster_config(&cfg, at, plan.grid, plan.smem, st);
+    CVB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN>, tmX, tmDY, plan.p));
+  } else {
+    conv_wgrad_kernel<BN><<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
+  }
   CVB_LAUNCH_CHECK();
   return CVB_OK;
 }

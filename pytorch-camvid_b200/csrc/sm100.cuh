@@ -97,6 +97,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// Multicast form: the box lands at the same shared-memory offset in every CTA of the cluster named by `mask`, and each of
+// them gets the bytes credited to ITS barrier at the same offset. One L2 -> SM transfer serves all of them.
+__device__ __forceinline__ void tma_load_4d_mcast(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3, int c4) {
   asm volatile(
@@ -168,6 +179,15 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t alo, ui
 // All previously issued MMAs of this thread arrive on `bar` when they retire (implies fence::before).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// The same, arriving on the barrier at this offset in every CTA of the cluster named by `mask` (single-CTA MMAs whose
+// operands were multicast: a stage may be refilled only when ALL its readers are done with it).
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 

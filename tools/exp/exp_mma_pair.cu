@@ -13,7 +13,7 @@ namespace cvb { void set_error(const char*, ...) {} int sm_count() { return 148;
 
 // walk != 0: consecutive iterations (4 MMAs = one 64-wide K chunk) read DIFFERENT A and B tiles, as a pipeline of TMA
 // stages does; walk == 0: the same B tile every time (what an operand cache, if there is one, would love).
-template <int N, bool PAIR>
+template <int N, bool PAIR, bool MN>
 __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int walk, int fill, const uint8_t* src) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -41,9 +41,11 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int wa
   const uint32_t tm = slot;
   if (warp == 1) {
     if (!PAIR || rank == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(PAIR ? 256 : 128, N, false, false);
+      // MN: both operands MN-major as in the weight-gradient kernels (a K = 16 slice = 16 rows of 128 B per 64-wide atom,
+      // atoms 8 KB apart, K groups of 8 rows 1 KB apart); else K-major as in the forward kernels
+      constexpr uint32_t idesc = idesc_bf16_f32(PAIR ? 256 : 128, N, MN, MN);
       constexpr uint32_t hi = desc_hi_sw128(1024);
-      const uint32_t a0 = desc_lo(smem_u32(smem), 16), b0 = desc_lo(smem_u32(smem + 32768), 16);
+      const uint32_t a0 = desc_lo(smem_u32(smem), MN ? 8192 : 16), b0 = desc_lo(smem_u32(smem + 32768), MN ? 8192 : 16);
       long long t0 = clock64();
       for (int i = 0; i < iters; ++i) {
         constexpr uint32_t b_tile = (PAIR ? N / 2 : N) * 128;  // bytes of B one SM holds per K chunk
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int wa
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (PAIR) umma_bf16_lohi_pair(d, aa + 2 * k, hi, bb + 2 * k, hi, idesc, 1u);
-            else umma_bf16_lohi(d, aa + 2 * k, hi, bb + 2 * k, hi, idesc, 1u);
+            if (PAIR) umma_bf16_lohi_pair(d, aa + (MN ? 128 : 2) * k, hi, bb + (MN ? 128 : 2) * k, hi, idesc, 1u);
+            else umma_bf16_lohi(d, aa + (MN ? 128 : 2) * k, hi, bb + (MN ? 128 : 2) * k, hi, idesc, 1u);
           }
         }
         __syncwarp();
@@ -108,9 +110,9 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int iters, int wa
   }
 }
 
-template <int N, bool PAIR>
+template <int N, bool PAIR, bool MN>
 void run(long long* d, int grid, int walk, int fill, const uint8_t* src) {
-  auto kern = rate<N, PAIR>;
+  auto kern = rate<N, PAIR, MN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 2000;
   cudaError_t e = cudaSuccess;
@@ -134,8 +136,8 @@ void run(long long* d, int grid, int walk, int fill, const uint8_t* src) {
   const long long h = hh[0];
   const double clk = double(h) / (iters * 4);
   // per-SM MACs of one instruction: 128 x N x 16 in both forms (the pair's M = 256 is split over two SMs)
-  printf("%s N=%3d %s fill %d (%.0f B/clk written by bulk copies): %s  %.1f clk per MMA; per SM: tensor pipe needs %d, operand rows A 128 + B %d -> model %.0f clk\n",
-         PAIR ? "pair M=256" : "single M=128", N, walk ? "walking tiles" : "same B tile  ", fill, fill ? double(hh[1]) * 16384 / double(h) : 0.0, cudaGetErrorString(e), clk, N / 2, PAIR ? N / 2 : N,
+  printf("%s %s N=%3d %s fill %d (%.0f B/clk written by bulk copies): %s  %.1f clk per MMA; per SM: tensor pipe needs %d, operand rows A 128 + B %d -> model %.0f clk\n",
+         MN ? "MN-major" : "K-major ", PAIR ? "pair M=256" : "single M=128", N, walk ? "walking tiles" : "same B tile  ", fill, fill ? double(hh[1]) * 16384 / double(h) : 0.0, cudaGetErrorString(e), clk, N / 2, PAIR ? N / 2 : N,
          0.44 * (128 + (PAIR ? N / 2 : N)));
 }
 
@@ -145,12 +147,18 @@ int main() {
   uint8_t* src;
   cudaMalloc(&src, 512 * 16384);
   cudaMemset(src, 0x3c, 512 * 16384);
-  for (int fill : {0, 1, 2, 4}) {
-    run<64, false>(d, 148, 1, fill, src);
-    run<128, false>(d, 148, 1, fill, src);
-    run<256, false>(d, 148, 1, fill, src);
-    run<128, true>(d, 148, 1, fill, src);
-    run<256, true>(d, 148, 1, fill, src);
+  for (int fill : {0, 4}) {
+    run<64, false, false>(d, 148, 1, fill, src);
+    run<128, false, false>(d, 148, 1, fill, src);
+    run<256, false, false>(d, 148, 1, fill, src);
+    run<128, true, false>(d, 148, 1, fill, src);
+    run<256, true, false>(d, 148, 1, fill, src);
+    run<64, false, true>(d, 148, 1, fill, src);
+    run<128, false, true>(d, 148, 1, fill, src);
+    run<192, false, true>(d, 148, 1, fill, src);
+    run<256, false, true>(d, 148, 1, fill, src);
+    run<128, true, true>(d, 148, 1, fill, src);
+    run<256, true, true>(d, 148, 1, fill, src);
   }
   return 0;
 }
