@@ -57,6 +57,7 @@ struct WgradParams {
   // v) on two neighbouring ci tiles (2t, 2t + 1) of the same (co tile, tap group): they read the same dy tiles, so each
   // fetches half of them and multicasts. Items, n_ci_tiles, grids and parts are then counted in virtual CTAs / tile pairs.
   int cluster;
+  int pair;  // cluster == 2 only: 1 = the CTA-pair instantiation (cta_group::2), 0 = two single-CTA MMAs sharing dy by multicast
   int patch_stride, dy_bytes;  // conv_wgrad_kernel: bytes between the ci chunks of a stage's x patch / its 64-channel dy units
   float* ws;  // [slots][taps][cin_pad][cout_pad]; part k of an item lives in slot k (k < parts of that item)
 };
@@ -72,10 +73,10 @@ __host__ __device__ inline int sk_owner(long long U, int G, long long u) {  // t
 
 // Issues every K slice of one pixel tile for ACCS accumulators (compile-time: no per-MMA predication; a k-step is one
 // 32-bit add on each descriptor low word).
-template <int BN, int ACCS>
+template <int BN, int ACCS, bool PAIR>
 __device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t x_lo, uint32_t d_lo, const uint32_t (&acc_lo)[kMaxAccs],
                                            int slices, uint32_t first) {
-  constexpr uint32_t idesc = idesc_bf16_f32(128, BN, true, true);
+  constexpr uint32_t idesc = idesc_bf16_f32(PAIR ? 256 : 128, BN, true, true);
   constexpr uint32_t a_hi = desc_hi_sw128(kWPitch * 128);  // K groups: consecutive tile rows of the patch
   constexpr uint32_t b_hi = desc_hi_sw128(kWTileW * 128);  // dy tile rows are dense
 #pragma unroll 1
@@ -83,17 +84,28 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t x_lo, ui
     const uint32_t xs = x_lo + s * (2 * kWPitch * 8), ds = d_lo + s * (2 * kWTileW * 8);
     const uint32_t accum = (first | static_cast<uint32_t>(s)) != 0 ? 1u : 0u;
 #pragma unroll
-    for (int j = 0; j < ACCS; ++j) umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+    for (int j = 0; j < ACCS; ++j) {
+      if (PAIR) umma_bf16_lohi_pair(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+      else umma_bf16_lohi(tmem_base + j * BN, xs + acc_lo[j], a_hi, ds, b_hi, idesc, accum);
+    }
   }
 }
 
-template <int BN>
+// PAIR: the two CTAs of a cluster run ONE M = 256 MMA (cta_group::2) on the two ci tiles they own: each supplies its own x
+// patch (its 128 A rows) and only HALF of the dy tile (BN / 2 of the N columns), the leader (cluster rank 0) issues, and
+// each CTA's TMEM receives its own 128 accumulator rows -- the epilogue and the workspace layout do not change. What
+// changes is the number of bytes DELIVERED to an SM per MAC (x + dy / 2 instead of x + dy: -28 % at BN = 256, -20 % at 128),
+// which is what bounds this kernel (42-45 B/clk per SM when all SMs pull; multicast into both CTAs delivers the same bytes
+// and gained nothing: profiles/r02z_wgrad_cluster.txt). Protocol as in conv_fprop_halo2_kernel: loads of both CTAs are
+// credited to the LEADER's full barrier, the leader's commits are multicast to both CTAs' empty / tfull barriers, both
+// epilogues report to the leader's tempty.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int b_units = BN / 64;
+  constexpr int b_units = PAIR ? BN / 128 : BN / 64;  // 64-channel dy boxes this CTA holds per stage
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
@@ -121,16 +133,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], cl);  // a stage is free when every CTA of the cluster that it was multicast to has consumed it
+      mbar_init(&full[i], PAIR ? 2 : 1);  // PAIR: the leader's expect_tx + the peer's "my loads are issued"
+      // a stage is free when every CTA of the cluster that it was multicast to has consumed it (PAIR: one multicast commit)
+      mbar_init(&empty[i], PAIR ? 1 : cl);
     }
     mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
+    mbar_init(tempty, PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs report to the leader
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -162,15 +180,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint8_t* sX = smem + stage * p.stage_bytes;
           uint8_t* sD = sX + p.CM * p.patch_stride;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx_bytes);
-          for (int c = 0; c < p.CM; ++c)
-            tma_load_4d(sX + c * p.patch_stride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
+          if (PAIR) {
+            if (crank == 0) mbar_expect_tx(&full[stage], 2 * tx_bytes);  // both CTAs' boxes are credited to the leader
+            for (int c = 0; c < p.CM; ++c)
+              tma_load_4d_pair(sX + c * p.patch_stride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
 #pragma unroll
-          for (int j = 0; j < b_units; ++j) {
-            if (cl == 1)
-              tma_load_4d(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
-            else if ((j & 1) == crank)  // this CTA's half of the dy tile, delivered to both CTAs
-              tma_load_4d_mcast(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0, 3);
+            for (int j = 0; j < b_units; ++j)  // this CTA's half of the N columns
+              tma_load_4d_pair(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + crank * (BN / 2) + j * 64, w0, h0, n0);
+            if (crank != 0) mbar_arrive_leader(&full[stage]);
+          } else {
+            mbar_expect_tx(&full[stage], tx_bytes);
+            for (int c = 0; c < p.CM; ++c)
+              tma_load_4d(sX + c * p.patch_stride, &tmX, &full[stage], (ci_tile * p.CM + c) * 64, w0 - 1, h0 - 1, n0);
+#pragma unroll
+            for (int j = 0; j < b_units; ++j) {
+              if (cl == 1)
+                tma_load_4d(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0);
+              else if ((j & 1) == crank)  // this CTA's half of the dy tile, delivered to both CTAs
+                tma_load_4d_mcast(sD + j * p.dy_bytes, &tmDY, &full[stage], co_tile * BN + j * 64, w0, h0, n0, 3);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -180,8 +208,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer (whole warp, one elected lane issues) -------------------------------
+  } else if (warp == 1 && (!PAIR || crank == 0)) {
+    // ------------------------------- MMA issuer (whole warp, one elected lane issues; PAIR: the leader CTA only) -------
     const uint32_t x_lo0 = desc_lo(smem_u32(smem), 0);
     const uint32_t d_lo0 = desc_lo(smem_u32(smem) + p.CM * p.patch_stride, p.dy_bytes);
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
@@ -225,16 +253,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t first = tile != tile_begin ? 1u : 0u;
         if (elect_one()) {
           switch (accs) {
-            case 1: issue_tile<BN, 1>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 2: issue_tile<BN, 2>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 3: if (3 * BN <= 512) issue_tile<BN, 3>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 4: if (4 * BN <= 512) issue_tile<BN, 4>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 5: if (5 * BN <= 512) issue_tile<BN, 5>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 6: if (6 * BN <= 512) issue_tile<BN, 6>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            case 7: if (7 * BN <= 512) issue_tile<BN, 7>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
-            default: if (8 * BN <= 512) issue_tile<BN, 8>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 1: issue_tile<BN, 1, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 2: issue_tile<BN, 2, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 3: if (3 * BN <= 512) issue_tile<BN, 3, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 4: if (4 * BN <= 512) issue_tile<BN, 4, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 5: if (5 * BN <= 512) issue_tile<BN, 5, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 6: if (6 * BN <= 512) issue_tile<BN, 6, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            case 7: if (7 * BN <= 512) issue_tile<BN, 7, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
+            default: if (8 * BN <= 512) issue_tile<BN, 8, PAIR>(tmem_base, x_lo, d_lo, acc_lo, slices, first); break;
           }
-          if (cl == 1) umma_commit(&empty[stage]);
+          if (PAIR) umma_commit_pair(&empty[stage]);
+          else if (cl == 1) umma_commit(&empty[stage]);
           else umma_commit_mcast(&empty[stage], 3);
         }
         __syncwarp();
@@ -243,7 +272,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(tfull);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(tfull);
+        else umma_commit(tfull);
+      }
       __syncwarp();
     }
     }
@@ -296,7 +328,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tempty);
+        else mbar_arrive(tempty);
+      }
     }
     }
   }
@@ -307,7 +342,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (cl == 2) cluster_sync_all();  // neither CTA leaves while the peer's multicasts / commits may still target it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -607,7 +643,7 @@ struct WgradPlan {
   long long ws_bytes;
 };
 
-static int wgrad_max_clusters(int BN);
+static int wgrad_max_clusters(int BN, bool pair);
 
 static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan* plan) {
   CVB_REQUIRE(taps == 9 || taps == 1, CVB_ERR_INVALID_ARG, "conv_wgrad: taps must be 9 or 1 (got %d)", taps);
@@ -698,19 +734,13 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.n_tap_groups = (taps + p.T - 1) / p.T;
   p.n_co_tiles = cout_pad / BN;
   p.n_ci_tiles = cin_pad / (64 * p.CM);
-  // shared-memory slots of a stage follow the tile height (1 KB granularity: swizzle atoms): shorter tiles = smaller stages
-  // = a deeper pipeline within the same 225 KB
-  p.patch_stride = ((p.th + 2) * kWPitch * 128 + 1023) / 1024 * 1024;
-  p.dy_bytes = p.th * kWTileW * 128;
-  p.stage_bytes = p.CM * p.patch_stride + (BN / 64) * p.dy_bytes;
-  p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
-  if (p.stages > 6) p.stages = 6;
-  CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
-  // Cluster of two along ci (CVB_WGRAD_CLUSTER=1): neighbouring ci tiles of one (co tile, tap group) read the same dy
-  // tiles; as a cluster each fetches half of them and multicasts, which takes 20-30 % off the L2 -> SM fill traffic the
-  // kernel is bound by (45 B/clk per SM is what the fabric delivers when all SMs pull: tools/exp/exp_mma_pair.cu; the
-  // BN = 256 pipeline asks for 54). Needs dy tiles of >= 2 boxes and an even number of ci tiles.
+  // Cluster of two along ci (CVB_WGRAD_CLUSTER = 1 or 2): neighbouring ci tiles of one (co tile, tap group) read the same dy
+  // tiles. 1 = each CTA fetches half of them and multicasts (fewer L2 reads, same bytes delivered per SM: measured neutral);
+  // 2 = the two CTAs run one M = 256 MMA as a pair and each keeps only HALF of the dy tile (fewer bytes delivered per SM,
+  // the bound of this kernel: 42-45 B/clk per SM is what arrives when all SMs pull, the BN = 256 pipeline asks for 54).
+  // Needs dy tiles of >= 2 boxes and an even number of ci tiles.
   int G = sm_count();
+  p.pair = 0;
   {
     static int want = -1;
     if (want < 0) {
@@ -718,14 +748,23 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
       want = e ? atoi(e) : 0;
     }
     if (want && BN >= 128 && (p.n_ci_tiles % 2) == 0 && (G % 2) == 0) {
-      const int pairs = wgrad_max_clusters(BN);
+      const int pairs = wgrad_max_clusters(BN, want == 2);
       if (pairs > 0) {
         p.cluster = 2;
+        p.pair = want == 2 ? 1 : 0;
         p.n_ci_tiles /= 2;
         G = pairs < G / 2 ? pairs : G / 2;
       }
     }
   }
+  // shared-memory slots of a stage follow the tile height (1 KB granularity: swizzle atoms): shorter tiles = smaller stages
+  // = a deeper pipeline within the same 225 KB; a CTA of a pair holds half of the dy tile
+  p.patch_stride = ((p.th + 2) * kWPitch * 128 + 1023) / 1024 * 1024;
+  p.dy_bytes = p.th * kWTileW * 128;
+  p.stage_bytes = p.CM * p.patch_stride + (BN / 64) / (p.pair ? 2 : 1) * p.dy_bytes;
+  p.stages = (kWgradSmemBudget - 2048) / p.stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  CVB_REQUIRE(p.stages >= 2, CVB_ERR_UNSUPPORTED, "conv_wgrad: stage of %d bytes does not pipeline", p.stage_bytes);
   p.items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
   p.total_units = 1LL * p.items * p.total_tiles;
   // Work partition. Stream-K: the (item, pixel tile) space is flattened and cut into equal contiguous ranges, one per
@@ -782,11 +821,11 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   return CVB_OK;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int configure_wgrad() {
   static bool configured = false;
   if (!configured) {
-    CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kWgradSmemBudget));
     configured = true;
   }
@@ -808,40 +847,50 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int
 }
 
 // How many 2-CTA clusters of the weight-gradient kernel the device runs at once (1 CTA per SM: the two CTAs of a cluster
-// need two free SMs of one GPC); 0 if clusters cannot be used. Asked once per tile width.
-template <int BN>
+// need two free SMs of one GPC); 0 if clusters cannot be used. Asked once per instantiation.
+template <int BN, bool PAIR>
 static int max_clusters_bn() {
   static int cached = -1;
   if (cached < 0) {
     cached = 0;
-    if (configure_wgrad<BN>() == CVB_OK) {
+    if (configure_wgrad<BN, PAIR>() == CVB_OK) {
       cudaLaunchConfig_t cfg;
       cudaLaunchAttribute at[1];
       cluster_config(&cfg, at, sm_count(), kWgradSmemBudget, nullptr);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_wgrad_kernel<BN>, &cfg) == cudaSuccess) cached = n;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_wgrad_kernel<BN, PAIR>, &cfg) == cudaSuccess) cached = n;
       else (void)cudaGetLastError();
     }
   }
   return cached;
 }
 
-static int wgrad_max_clusters(int BN) { return BN == 256 ? max_clusters_bn<256>() : (BN == 128 ? max_clusters_bn<128>() : 0); }
+static int wgrad_max_clusters(int BN, bool pair) {
+  if (BN == 256) return pair ? max_clusters_bn<256, true>() : max_clusters_bn<256, false>();
+  if (BN == 128) return pair ? max_clusters_bn<128, true>() : max_clusters_bn<128, false>();
+  return 0;
+}
 
-template <int BN>
-static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
-  int rc = configure_wgrad<BN>();
+template <int BN, bool PAIR>
+static int launch_wgrad_as(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
+  int rc = configure_wgrad<BN, PAIR>();
   if (rc) return rc;
   if (plan.p.cluster == 2) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     cluster_config(&cfg, at, plan.grid, plan.smem, st);
-    CVB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN>, tmX, tmDY, plan.p));
+    CVB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, PAIR>, tmX, tmDY, plan.p));
   } else {
-    conv_wgrad_kernel<BN><<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
+    conv_wgrad_kernel<BN, PAIR><<<plan.grid, kWgradThreads, plan.smem, st>>>(tmX, tmDY, plan.p);
   }
   CVB_LAUNCH_CHECK();
   return CVB_OK;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPlan& plan, cudaStream_t st) {
+  if (BN >= 128 && plan.p.pair) return launch_wgrad_as<(BN >= 128 ? BN : 128), true>(tmX, tmDY, plan, st);
+  return launch_wgrad_as<BN, false>(tmX, tmDY, plan, st);
 }
 
 }  // namespace cvb
