@@ -26,4 +26,3 @@ t("write only (fill_)", lambda: b.fill_(1.0), n)
 t("write only (cudaMemset)", lambda: b.view(torch.uint8).zero_(), n)
 t("read only (sum fp32 view)", lambda: a.view(torch.float32).sum(), n)
 t("copy (read + write)", lambda: b.copy_(a), 2 * n)
-t("1 read : 4 write (repeat)", lambda: torch.repeat_interleave(a[: n // 8], 4, out=b), n // 4 + n)
