@@ -691,7 +691,14 @@ static int plan_wgrad(const cvb_view& x, const cvb_view& dy, int taps, WgradPlan
   p.taps = taps;
   p.cin_pad = cin_pad;
   p.cout_pad = cout_pad;
-  const int BN = (cout_pad % 256 == 0) ? 256 : ((cout_pad % 128 == 0) ? 128 : 64);
+  // CVB_WGRAD_BN=128: N = 128 tiles also where cout is a multiple of 256 (3 taps x 128 columns per item instead of 2 x 256:
+  // fewer operand bytes per MAC, twice the co tiles) -- A/B knob
+  static int bn_cap = -1;
+  if (bn_cap < 0) {
+    const char* e = getenv("CVB_WGRAD_BN");
+    bn_cap = e ? atoi(e) : 256;
+  }
+  const int BN = (cout_pad % 256 == 0 && bn_cap >= 256) ? 256 : ((cout_pad % 128 == 0) ? 128 : 64);
   plan->BN = BN;
   // CVB_WGRAD_RS=0 keeps the N = 64 kernel for cout = 64 (A/B measurements); read per call
   const char* rs_env = getenv("CVB_WGRAD_RS");
